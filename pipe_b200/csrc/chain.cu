@@ -1,0 +1,895 @@
+// chain.cu -- the pb_chain object: planning a run of Processors into fused
+// segments, carried state, launches, and the host-marshalling paths.
+//
+// Reference boundary: a pb_chain is what a ProcessorAllocatorFunc
+// (reference line.go:30) would allocate for a contiguous run of GPU Processors,
+// and pb_chain_process* is the body of the resulting ProcessFunc
+// (pipe.go:64, invoked from Processor.execute at pipe.go:438).
+#include <cmath>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "chain_tile.cuh"
+
+namespace pb {
+
+struct StageCopy {
+    pb_stage_desc d{};
+    std::vector<double> taps;
+};
+
+struct Segment {
+    int fir_stage = -1, bq_stage = -1, rs_stage = -1;
+    std::vector<std::pair<int, int>> gain_stages;  // (stage index, gain point 0..3)
+    // shape
+    int Hf = 0, Hr = 0, P = 0, up = 1, down = 1;
+    int L = 0, FB = 0, tp_len = 0, tp_off = 0, wt_len = 0, apow_len = 0;
+    size_t smem = 0;
+    int grid_max = 0;
+    // coefficient tables (device)
+    void *d_taps = nullptr, *d_wt = nullptr, *d_apow = nullptr, *d_coef = nullptr;
+    // carried state, ping-ponged
+    void *d_xhist[2] = {nullptr, nullptr}, *d_yhist[2] = {nullptr, nullptr}, *d_state[2] = {nullptr, nullptr};
+    int pp = 0;
+    int64_t acc = 0;
+    // look-back workspace
+    void *d_agg = nullptr, *d_inc = nullptr;
+    unsigned *d_status = nullptr;
+    int lb_tiles = 0;
+    // parameters (host, double)
+    double g[4] = {1, 1, 1, 1};
+    double b[3] = {1, 0, 0}, a[2] = {0, 0};
+};
+
+struct Slot {  // one in-flight batch of the pipelined host path
+    void *h_in = nullptr, *h_out = nullptr;  // pinned staging
+    void *d_in = nullptr, *d_out = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
+    std::vector<int64_t> out_counts;
+    void *user_out = nullptr;  // pageable destination to fill at collect (nullptr when D2H went direct)
+    int64_t out_frames = 0;
+    bool busy = false;
+};
+
+}  // namespace pb
+
+using namespace pb;
+
+struct pb_chain {
+    int device = 0, dtype = PB_F32, C = 0, buffer_frames = 0, max_batch = 1;
+    unsigned flags = 0;
+    double sample_rate = 0, out_sample_rate = 0;
+    size_t elem = 4;
+    int64_t max_frames = 0;
+    int num_sms = 148;
+    std::vector<StageCopy> stages;
+    std::vector<Segment> segs;
+    void *d_mid[2] = {nullptr, nullptr};
+    unsigned long long *d_ticket = nullptr;  // [0] ticket counter, [1] low word = kernel error flag
+    unsigned long long ticket_base = 0;
+    unsigned epoch = 0;
+    double *d_meter = nullptr;  // [2][C]: peak, sumsq
+    int64_t meter_frames = 0;
+    cudaStream_t st_compute = nullptr, st_h2d = nullptr, st_d2h = nullptr;
+    Slot slots[2];
+    int slot_head = 0, slot_tail = 0, slots_busy = 0;
+    int last_path = 0;
+    int64_t launches = 0;
+};
+
+namespace pb {
+
+// ------------------------------------------------------------------ helpers --
+
+template <typename T>
+static cudaError_t upload(void *dst, const std::vector<double> &v)
+{
+    std::vector<T> tmp(v.size());
+    for (size_t i = 0; i < v.size(); i++) tmp[i] = (T)v[i];
+    return cudaMemcpy(dst, tmp.data(), sizeof(T) * tmp.size(), cudaMemcpyHostToDevice);
+}
+
+static cudaError_t upload_any(int dtype, void *dst, const std::vector<double> &v)
+{
+    return dtype == PB_F32 ? upload<float>(dst, v) : upload<double>(dst, v);
+}
+
+static int32_t validate_stage(const pb_stage_desc &s, int idx)
+{
+    switch (s.kind) {
+    case PB_STAGE_COPY:
+    case PB_STAGE_GAIN:
+        if (!std::isfinite(s.gain) && s.kind == PB_STAGE_GAIN) return fail(PB_ERR_INVALID, "stage %d: gain is not finite", idx);
+        return PB_OK;
+    case PB_STAGE_BIQUAD:
+        for (int i = 0; i < 3; i++)
+            if (!std::isfinite(s.b[i])) return fail(PB_ERR_INVALID, "stage %d: biquad b[%d] is not finite", idx, i);
+        for (int i = 0; i < 2; i++)
+            if (!std::isfinite(s.a[i])) return fail(PB_ERR_INVALID, "stage %d: biquad a[%d] is not finite", idx, i);
+        return PB_OK;
+    case PB_STAGE_FIR:
+        if (s.n_taps < 1 || !s.taps) return fail(PB_ERR_INVALID, "stage %d: FIR needs n_taps >= 1 and taps", idx);
+        return PB_OK;
+    case PB_STAGE_RESAMPLE:
+        if (s.up < 1 || s.down < 1 || !s.taps || s.n_taps < s.up || s.n_taps % s.up != 0)
+            return fail(PB_ERR_INVALID, "stage %d: resample needs up,down >= 1 and n_taps a multiple of up", idx);
+        if (s.up > s.down)
+            return fail(PB_ERR_UNSUPPORTED,
+                        "stage %d: resample up > down would emit more frames than bufferSize (pipe.go:437-443)", idx);
+        return PB_OK;
+    default:
+        return fail(PB_ERR_INVALID, "stage %d: unknown kind %d", idx, s.kind);
+    }
+}
+
+// Cut the stage list into fused segments [gain*][FIR]?[gain*][biquad]?[gain*][resample]?[gain*].
+static void plan_segments(pb_chain *c)
+{
+    c->segs.clear();
+    Segment cur;
+    int rank_used = 0;  // 0 none, 1 FIR, 2 biquad, 3 resample
+    for (int i = 0; i < (int)c->stages.size(); i++) {
+        const pb_stage_desc &s = c->stages[i].d;
+        if (s.kind == PB_STAGE_COPY) continue;
+        if (s.kind == PB_STAGE_GAIN) {
+            cur.gain_stages.push_back({i, rank_used});
+            continue;
+        }
+        const int rank = s.kind == PB_STAGE_FIR ? 1 : s.kind == PB_STAGE_BIQUAD ? 2 : 3;
+        if (rank <= rank_used) {
+            c->segs.push_back(cur);
+            cur = Segment();
+            rank_used = 0;
+        }
+        if (rank == 1) cur.fir_stage = i;
+        if (rank == 2) cur.bq_stage = i;
+        if (rank == 3) cur.rs_stage = i;
+        rank_used = rank;
+    }
+    c->segs.push_back(cur);
+}
+
+static void free_segment(Segment &s)
+{
+    void *ptrs[] = {s.d_taps, s.d_wt, s.d_apow, s.d_coef, s.d_xhist[0], s.d_xhist[1], s.d_yhist[0], s.d_yhist[1],
+                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+}
+
+template <typename T, int FB>
+static int32_t configure_kernel(pb_chain *c, Segment &s)
+{
+    auto kern = chain_tile_kernel<T, FB>;
+    // the attribute is per function, not per chain: always raise it to the architectural maximum
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    int per_sm = 0;
+    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, s.smem));
+    if (per_sm < 1) return fail(PB_ERR_UNSUPPORTED, "fused tile kernel does not fit on an SM (%zu B shared)", s.smem);
+    s.grid_max = per_sm * c->num_sms;
+    return PB_OK;
+}
+
+// (Re)compute the parameter-dependent tables of one segment and upload them.
+static int32_t refresh_segment_params(pb_chain *c, Segment &s)
+{
+    for (int i = 0; i < 4; i++) s.g[i] = 1.0;
+    for (auto &gs : s.gain_stages) s.g[gs.second] *= c->stages[gs.first].d.gain;
+    if (s.fir_stage >= 0) {
+        const auto &st = c->stages[s.fir_stage];
+        std::vector<double> tp((size_t)s.tp_len, 0.0);
+        for (int k = 0; k < (int)st.taps.size(); k++) tp[(size_t)k + s.tp_off] = st.taps[k];
+        PB_CUDA(upload_any(c->dtype, s.d_taps, tp));
+    }
+    if (s.bq_stage >= 0) {
+        const pb_stage_desc &d = c->stages[s.bq_stage].d;
+        for (int i = 0; i < 3; i++) s.b[i] = d.b[i];
+        for (int i = 0; i < 2; i++) s.a[i] = d.a[i];
+        // TDF-II as a state-space system: s' = A s + B x, y = s[0] + b0 x
+        const double A[4] = {-s.a[0], 1.0, -s.a[1], 0.0};
+        const double B[2] = {s.b[1] - s.a[0] * s.b[0], s.b[2] - s.a[1] * s.b[0]};
+        std::vector<double> apow((size_t)s.apow_len * 4), wt((size_t)s.wt_len * 2);
+        double M[4] = {1, 0, 0, 1};
+        for (int k = 0; k < s.apow_len; k++) {
+            for (int i = 0; i < 4; i++) apow[(size_t)k * 4 + i] = M[i];
+            if (k < s.wt_len) {
+                wt[(size_t)k * 2] = M[0] * B[0] + M[1] * B[1];
+                wt[(size_t)k * 2 + 1] = M[2] * B[0] + M[3] * B[1];
+            }
+            const double N[4] = {M[0] * A[0] + M[1] * A[2], M[0] * A[1] + M[1] * A[3],
+                                 M[2] * A[0] + M[3] * A[2], M[2] * A[1] + M[3] * A[3]};
+            for (int i = 0; i < 4; i++) M[i] = N[i];
+        }
+        PB_CUDA(upload_any(c->dtype, s.d_apow, apow));
+        PB_CUDA(upload_any(c->dtype, s.d_wt, wt));
+    }
+    if (s.rs_stage >= 0) {
+        const auto &st = c->stages[s.rs_stage];
+        std::vector<double> coef((size_t)s.up * s.P);
+        for (int br = 0; br < s.up; br++)
+            for (int k = 0; k < s.P; k++) coef[(size_t)br * s.P + k] = st.taps[(size_t)br + (size_t)k * s.up];
+        PB_CUDA(upload_any(c->dtype, s.d_coef, coef));
+    }
+    return PB_OK;
+}
+
+static int32_t build_segment(pb_chain *c, Segment &s)
+{
+    const bool f32 = c->dtype == PB_F32;
+    const size_t el = c->elem;
+    s.FB = f32 ? 16 : 8;
+    if (s.fir_stage >= 0) s.Hf = c->stages[s.fir_stage].d.n_taps - 1;
+    if (s.rs_stage >= 0) {
+        const pb_stage_desc &d = c->stages[s.rs_stage].d;
+        s.up = d.up;
+        s.down = d.down;
+        s.P = d.n_taps / d.up;
+        s.Hr = s.P - 1;
+    }
+    const bool has_fir = s.fir_stage >= 0;
+    // tile length
+    auto smem_for = [&](int L) {
+        const int tp_len = has_fir ? (s.Hf + 1) + 2 * s.FB + s.FB : 0;
+        const int wt_len = (L + s.Hr) / kNW + 2;
+        return f32 ? TileSmem<float>(L, s.Hf, s.Hr, has_fir, tp_len, wt_len, s.FB).total
+                   : TileSmem<double>(L, s.Hf, s.Hr, has_fir, tp_len, wt_len, s.FB).total;
+    };
+    if (has_fir) {
+        int rows = kNW * s.FB * 2;
+        while (rows <= s.Hr * 2) rows += kNW * s.FB;
+        if (smem_for(rows - s.Hr) > 110 * 1024 && rows - kNW * s.FB > s.Hr * 2) rows -= kNW * s.FB;
+        s.L = rows - s.Hr;
+    } else {
+        s.L = f32 ? 256 : 128;
+        while (s.L <= s.Hr * 2) s.L *= 2;
+    }
+    s.tp_off = 2 * s.FB;
+    s.tp_len = has_fir ? (s.Hf + 1) + s.tp_off + s.FB : 0;
+    s.wt_len = (s.L + s.Hr) / kNW + 2;
+    s.apow_len = s.L + s.Hr + 1;
+    s.smem = smem_for(s.L);
+    if (s.smem > 227 * 1024)
+        return fail(PB_ERR_UNSUPPORTED, "FIR with %d taps needs %zu B of shared memory per tile (max 232448)", s.Hf + 1, s.smem);
+    if (f32) {
+        int32_t r = configure_kernel<float, 16>(c, s);
+        if (r != PB_OK) return r;
+    } else {
+        int32_t r = configure_kernel<double, 8>(c, s);
+        if (r != PB_OK) return r;
+    }
+    // tables
+    if (has_fir) PB_CUDA(cudaMalloc(&s.d_taps, el * (size_t)s.tp_len));
+    if (s.bq_stage >= 0) {
+        PB_CUDA(cudaMalloc(&s.d_apow, el * (size_t)s.apow_len * 4));
+        PB_CUDA(cudaMalloc(&s.d_wt, el * (size_t)s.wt_len * 2));
+        s.lb_tiles = (int)ceil_div64(c->max_frames, s.L) + 1;
+        const size_t groups = (size_t)(c->C + kCg - 1) / kCg;
+        PB_CUDA(cudaMalloc(&s.d_agg, el * groups * s.lb_tiles * 64));
+        PB_CUDA(cudaMalloc(&s.d_inc, el * groups * s.lb_tiles * 64));
+        PB_CUDA(cudaMalloc((void **)&s.d_status, sizeof(unsigned) * groups * s.lb_tiles));
+        PB_CUDA(cudaMemset(s.d_status, 0, sizeof(unsigned) * groups * s.lb_tiles));
+    }
+    if (s.rs_stage >= 0) PB_CUDA(cudaMalloc(&s.d_coef, el * (size_t)s.up * s.P));
+    for (int i = 0; i < 2; i++) {
+        if (s.Hf > 0) {
+            PB_CUDA(cudaMalloc(&s.d_xhist[i], el * (size_t)s.Hf * c->C));
+            PB_CUDA(cudaMemset(s.d_xhist[i], 0, el * (size_t)s.Hf * c->C));
+        }
+        if (s.Hr > 0) {
+            PB_CUDA(cudaMalloc(&s.d_yhist[i], el * (size_t)s.Hr * c->C));
+            PB_CUDA(cudaMemset(s.d_yhist[i], 0, el * (size_t)s.Hr * c->C));
+        }
+        if (s.bq_stage >= 0) {
+            PB_CUDA(cudaMalloc(&s.d_state[i], el * (size_t)c->C * 2));
+            PB_CUDA(cudaMemset(s.d_state[i], 0, el * (size_t)c->C * 2));
+        }
+    }
+    return refresh_segment_params(c, s);
+}
+
+static int32_t reset_segment(pb_chain *c, Segment &s)
+{
+    const size_t el = c->elem;
+    for (int i = 0; i < 2; i++) {
+        if (s.d_xhist[i]) PB_CUDA(cudaMemsetAsync(s.d_xhist[i], 0, el * (size_t)s.Hf * c->C, c->st_compute));
+        if (s.d_yhist[i]) PB_CUDA(cudaMemsetAsync(s.d_yhist[i], 0, el * (size_t)s.Hr * c->C, c->st_compute));
+        if (s.d_state[i]) PB_CUDA(cudaMemsetAsync(s.d_state[i], 0, el * (size_t)c->C * 2, c->st_compute));
+    }
+    s.acc = 0;
+    return PB_OK;
+}
+
+// One fused launch: `n` input frames of segment `s` from `in` to `out`.
+template <typename T, int FB>
+static int32_t launch_segment(pb_chain *c, Segment &s, const void *in, int64_t n, void *out, bool is_last_segment,
+                              cudaStream_t stream)
+{
+    TileParams<T> p{};
+    p.in = (const T *)in;
+    p.out = (T *)out;
+    p.n_frames = n;
+    p.C = c->C;
+    p.L = s.L;
+    p.n_tiles = (int)ceil_div64(n, s.L);
+    p.n_groups = (c->C + kCg - 1) / kCg;
+    const bool has_fir = s.fir_stage >= 0, has_bq = s.bq_stage >= 0, has_rs = s.rs_stage >= 0;
+    // fold gains whose stage is absent into the previous present point (see TileParams)
+    double g_load = s.g[0], g_fir = s.g[1], g_bq = s.g[2], g_out = s.g[3];
+    if (!has_fir) { g_load *= g_fir; g_fir = 1.0; }
+    if (!has_bq) { (has_fir ? g_fir : g_load) *= g_bq; g_bq = 1.0; }
+    if (!has_rs) { (has_bq ? g_bq : has_fir ? g_fir : g_load) *= g_out; g_out = 1.0; }
+    p.g_load = (T)g_load; p.g_fir = (T)g_fir; p.g_bq = (T)g_bq; p.g_out = (T)g_out;
+    p.Hf = s.Hf;
+    p.has_fir = has_fir;
+    p.taps_padded = (const T *)s.d_taps;
+    p.tp_len = s.tp_len;
+    p.tp_off = s.tp_off;
+    p.xhist = (const T *)s.d_xhist[s.pp];
+    p.xhist_next = (T *)s.d_xhist[s.pp ^ 1];
+    p.has_bq = has_bq;
+    p.b0 = (T)s.b[0]; p.b1 = (T)s.b[1]; p.b2 = (T)s.b[2]; p.a1 = (T)s.a[0]; p.a2 = (T)s.a[1];
+    p.bq_wt = (const T *)s.d_wt;
+    p.bq_apow = (const T *)s.d_apow;
+    p.wt_len = s.wt_len;
+    p.bq_state = (const T *)s.d_state[s.pp];
+    p.bq_state_next = (T *)s.d_state[s.pp ^ 1];
+    p.lb_agg = (T *)s.d_agg;
+    p.lb_inc = (T *)s.d_inc;
+    p.lb_status = s.d_status;
+    c->epoch = (c->epoch % 0x3ffffffeu) + 1u;
+    p.epoch = c->epoch;
+    p.has_rs = has_rs;
+    p.rs_up = s.up; p.rs_down = s.down; p.rs_P = s.P; p.Hr = s.Hr;
+    p.rs_acc0 = s.acc;
+    p.rs_coef = (const T *)s.d_coef;
+    p.yhist = (const T *)s.d_yhist[s.pp];
+    p.yhist_next = (T *)s.d_yhist[s.pp ^ 1];
+    const bool meter = is_last_segment && (c->flags & PB_CHAIN_METER);
+    p.meter_peak = meter ? c->d_meter : nullptr;
+    p.meter_sumsq = meter ? c->d_meter + c->C : nullptr;
+    p.ticket = c->d_ticket;
+    p.ticket_base = c->ticket_base;
+    p.err_flag = reinterpret_cast<int *>(c->d_ticket + 1);
+    p.vec_ok = (sizeof(T) == 4 && c->C % 4 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+    if (has_bq && p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
+    const int64_t total = (int64_t)p.n_tiles * p.n_groups;
+    const int grid = (int)std::min<int64_t>(total, s.grid_max);
+    chain_tile_kernel<T, FB><<<grid, kTileThreads, s.smem, stream>>>(p);
+    PB_CUDA(cudaGetLastError());
+    c->ticket_base += (unsigned long long)total + (unsigned long long)grid;
+    c->launches++;
+    s.pp ^= 1;
+    return PB_OK;
+}
+
+// per-buffer output frame counts through every resampling segment (integer bookkeeping)
+static void count_outputs(pb_chain *c, const int64_t *buf_frames, int n_buffers, int64_t *buf_out, int64_t *total_in,
+                          int64_t *total_out, bool commit)
+{
+    std::vector<int64_t> acc(c->segs.size());
+    for (size_t i = 0; i < c->segs.size(); i++) acc[i] = c->segs[i].acc;
+    int64_t tin = 0, tout = 0;
+    for (int bi = 0; bi < n_buffers; bi++) {
+        int64_t n = buf_frames[bi];
+        tin += n;
+        for (size_t i = 0; i < c->segs.size(); i++) {
+            const Segment &s = c->segs[i];
+            if (s.rs_stage < 0) continue;
+            const int64_t tot = acc[i] + n * s.up;
+            n = tot / s.down;
+            acc[i] = tot % s.down;
+        }
+        if (buf_out) buf_out[bi] = n;
+        tout += n;
+    }
+    if (commit)
+        for (size_t i = 0; i < c->segs.size(); i++) c->segs[i].acc = acc[i];
+    *total_in = tin;
+    *total_out = tout;
+}
+
+static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *buf_frames, int n_buffers, void *out_dev,
+                                int64_t out_capacity_frames, int64_t *buf_out_frames, cudaStream_t stream)
+{
+    if (!buf_frames || n_buffers < 1) return fail(PB_ERR_INVALID, "process: need at least one buffer");
+    if (n_buffers > c->max_batch) return fail(PB_ERR_CAPACITY, "process: %d buffers > max_batch %d", n_buffers, c->max_batch);
+    for (int i = 0; i < n_buffers; i++) {
+        if (buf_frames[i] < 0 || buf_frames[i] > c->buffer_frames)
+            return fail(PB_ERR_INVALID, "process: buffer %d has %lld frames (bufferSize %d)", i, (long long)buf_frames[i], c->buffer_frames);
+        // only the final buffer of a stream may be short (Source.execute, pipe.go:404-406)
+        if (i + 1 < n_buffers && buf_frames[i] != c->buffer_frames)
+            return fail(PB_ERR_INVALID, "process: only the last buffer of a batch may be short");
+    }
+    int64_t tin = 0, tout = 0;
+    count_outputs(c, buf_frames, n_buffers, nullptr, &tin, &tout, false);
+    if (tout > out_capacity_frames) return fail(PB_ERR_CAPACITY, "process: output needs %lld frames, capacity %lld", (long long)tout, (long long)out_capacity_frames);
+    if (tin > 0 && (!in_dev || !out_dev)) return fail(PB_ERR_INVALID, "process: NULL buffer");
+    if (tin > 0) {
+        const void *src = in_dev;
+        int64_t n = tin;
+        for (size_t i = 0; i < c->segs.size(); i++) {
+            Segment &s = c->segs[i];
+            const bool lastseg = (i + 1 == c->segs.size());
+            void *dst = lastseg ? out_dev : c->d_mid[i & 1];
+            int32_t r = c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, src, n, dst, lastseg, stream)
+                                           : launch_segment<double, 8>(c, s, src, n, dst, lastseg, stream);
+            if (r != PB_OK) return r;
+            if (s.rs_stage >= 0) n = (s.acc + n * s.up) / s.down;  // s.acc is committed below, after every launch used it
+            src = dst;
+            if (n == 0 && !lastseg) {
+                // nothing left to feed downstream this call; later segments keep their state
+                break;
+            }
+        }
+        c->last_path = 1;
+    }
+    count_outputs(c, buf_frames, n_buffers, buf_out_frames, &tin, &tout, true);
+    c->meter_frames += tout;
+    return PB_OK;
+}
+
+}  // namespace pb
+
+// =============================================================================
+//                                   C-ABI
+// =============================================================================
+
+extern "C" int32_t pb_abi_version(void) { return PB_ABI_VERSION; }
+
+extern "C" const char *pb_last_error(void) { return tls_error_buf(); }
+
+extern "C" int32_t pb_chain_destroy(pb_chain *c)
+{
+    if (!c) return PB_OK;
+    DeviceGuard dg(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->segs) free_segment(s);
+    for (int i = 0; i < 2; i++) {
+        if (c->d_mid[i]) cudaFree(c->d_mid[i]);
+        Slot &sl = c->slots[i];
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        if (sl.h_out) cudaFreeHost(sl.h_out);
+        if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.d_out) cudaFree(sl.d_out);
+        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
+    }
+    if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_meter) cudaFree(c->d_meter);
+    if (c->st_compute) cudaStreamDestroy(c->st_compute);
+    if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
+    if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
+    delete c;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_create(const pb_chain_desc *desc, pb_chain **out)
+{
+    if (!desc || !out) return fail(PB_ERR_INVALID, "pb_chain_create: NULL argument");
+    *out = nullptr;
+    if (desc->abi_version != PB_ABI_VERSION) return fail(PB_ERR_INVALID, "pb_chain_create: abi_version %d != %d", desc->abi_version, PB_ABI_VERSION);
+    if (desc->dtype != PB_F32 && desc->dtype != PB_F64) return fail(PB_ERR_INVALID, "pb_chain_create: bad dtype");
+    if (desc->channels < 1 || desc->buffer_frames < 1 || desc->max_batch < 1 || desc->n_stages < 0 ||
+        (desc->n_stages > 0 && !desc->stages))
+        return fail(PB_ERR_INVALID, "pb_chain_create: bad channels/buffer_frames/max_batch/stages");
+    for (int i = 0; i < desc->n_stages; i++) {
+        int32_t r = validate_stage(desc->stages[i], i);
+        if (r != PB_OK) return r;
+    }
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev < 1)
+            return fail(PB_ERR_NO_DEVICE, "no CUDA device (%s); pipe_b200 has no CPU fallback", cudaGetErrorString(e));
+    }
+    if (desc->device < 0 || desc->device >= ndev) return fail(PB_ERR_INVALID, "pb_chain_create: device %d of %d", desc->device, ndev);
+    DeviceGuard dg(desc->device);
+    PB_CUDA(dg.err);
+    cudaDeviceProp prop{};
+    PB_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+    if (prop.major < 10)
+        return fail(PB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", desc->device, prop.major, prop.minor);
+
+    pb_chain *c = new (std::nothrow) pb_chain();
+    if (!c) return fail(PB_ERR_NOMEM, "out of host memory");
+    c->device = desc->device;
+    c->dtype = desc->dtype;
+    c->elem = desc->dtype == PB_F32 ? 4 : 8;
+    c->C = desc->channels;
+    c->buffer_frames = desc->buffer_frames;
+    c->max_batch = desc->max_batch;
+    c->flags = (unsigned)desc->flags;
+    c->sample_rate = desc->sample_rate;
+    c->max_frames = (int64_t)desc->buffer_frames * desc->max_batch;
+    c->num_sms = prop.multiProcessorCount;
+    c->stages.resize((size_t)desc->n_stages);
+    for (int i = 0; i < desc->n_stages; i++) {
+        c->stages[i].d = desc->stages[i];
+        if (desc->stages[i].taps && desc->stages[i].n_taps > 0)
+            c->stages[i].taps.assign(desc->stages[i].taps, desc->stages[i].taps + desc->stages[i].n_taps);
+        c->stages[i].d.taps = nullptr;  // never retain a caller pointer
+    }
+    auto bail = [&](int32_t r) {
+        char keep[512];
+        snprintf(keep, sizeof keep, "%s", tls_error_buf());
+        pb_chain_destroy(c);
+        snprintf(tls_error_buf(), 512, "%s", keep);
+        return r;
+    };
+#define PB_TRY(expr)                         \
+    do {                                     \
+        int32_t _r = (expr);                 \
+        if (_r != PB_OK) return bail(_r);    \
+    } while (0)
+#define PB_TRY_CUDA(expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return bail(fail(_e == cudaErrorMemoryAllocation ? PB_ERR_NOMEM : PB_ERR_CUDA, "%s failed: %s", #expr, \
+                             cudaGetErrorString(_e)));                                             \
+    } while (0)
+
+    PB_TRY_CUDA(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
+    PB_TRY_CUDA(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+    PB_TRY_CUDA(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+    PB_TRY_CUDA(cudaMalloc((void **)&c->d_ticket, 2 * sizeof(unsigned long long)));
+    PB_TRY_CUDA(cudaMemset(c->d_ticket, 0, 2 * sizeof(unsigned long long)));
+    if (c->flags & PB_CHAIN_METER) {
+        PB_TRY_CUDA(cudaMalloc((void **)&c->d_meter, sizeof(double) * 2 * (size_t)c->C));
+        PB_TRY_CUDA(cudaMemset(c->d_meter, 0, sizeof(double) * 2 * (size_t)c->C));
+    }
+    plan_segments(c);
+    double rate = c->sample_rate;
+    for (auto &s : c->segs) {
+        PB_TRY(build_segment(c, s));
+        if (s.rs_stage >= 0) rate = rate * s.up / s.down;
+    }
+    c->out_sample_rate = rate;
+    if (c->segs.size() > 1)
+        for (int i = 0; i < 2; i++) PB_TRY_CUDA(cudaMalloc(&c->d_mid[i], c->elem * (size_t)c->max_frames * c->C));
+    PB_TRY_CUDA(cudaDeviceSynchronize());
+#undef PB_TRY
+#undef PB_TRY_CUDA
+    *out = c;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_reset(pb_chain *c)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_reset: NULL chain");
+    if (c->slots_busy) return fail(PB_ERR_STATE, "pb_chain_reset: %d submitted batches not collected", c->slots_busy);
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaDeviceSynchronize());
+    for (auto &s : c->segs) {
+        int32_t r = reset_segment(c, s);
+        if (r != PB_OK) return r;
+    }
+    if (c->d_meter) PB_CUDA(cudaMemsetAsync(c->d_meter, 0, sizeof(double) * 2 * (size_t)c->C, c->st_compute));
+    c->meter_frames = 0;
+    PB_CUDA(cudaStreamSynchronize(c->st_compute));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_out_properties(const pb_chain *c, int32_t *channels, double *sample_rate)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_out_properties: NULL chain");
+    if (channels) *channels = c->C;
+    if (sample_rate) *sample_rate = c->out_sample_rate;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_peek_out_frames(const pb_chain *c, int64_t in_frames, int64_t *out_frames)
+{
+    if (!c || !out_frames || in_frames < 0) return fail(PB_ERR_INVALID, "pb_chain_peek_out_frames: bad argument");
+    int64_t n = in_frames;
+    for (const auto &s : c->segs)
+        if (s.rs_stage >= 0) n = (s.acc + n * s.up) / s.down;
+    *out_frames = n;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_process_batch_device(pb_chain *c, const void *in_dev, const int64_t *buf_frames,
+                                                 int32_t n_buffers, void *out_dev, int64_t out_capacity_frames,
+                                                 int64_t *buf_out_frames, void *stream)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_process_batch_device: NULL chain");
+    if (c->slots_busy) return fail(PB_ERR_STATE, "process while %d submitted batches are in flight", c->slots_busy);
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    return run_batch_device(c, in_dev, buf_frames, n_buffers, out_dev, out_capacity_frames, buf_out_frames,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int32_t pb_chain_sync(pb_chain *c, void *stream)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_sync: NULL chain");
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    PB_CUDA(cudaStreamSynchronize(c->st_compute));
+    int flag = 0;
+    PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return fail(PB_ERR_CUDA, "fused tile kernel: look-back wait timed out (kernel error flag set)");
+    return PB_OK;
+}
+
+static int32_t ensure_slot(pb_chain *c, Slot &sl)
+{
+    const size_t bytes = c->elem * (size_t)c->max_frames * c->C;
+    if (!sl.d_in) PB_CUDA(cudaMalloc(&sl.d_in, bytes));
+    if (!sl.d_out) PB_CUDA(cudaMalloc(&sl.d_out, bytes));
+    if (!sl.ev_h2d) PB_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+    if (!sl.ev_done) PB_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    if (!sl.ev_d2h) PB_CUDA(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
+    return PB_OK;
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int32_t pb_chain_pipeline_depth(const pb_chain *c) { return c ? 2 : 0; }
+
+extern "C" int32_t pb_chain_submit(pb_chain *c, const void *in_host, const int64_t *buf_frames, int32_t n_buffers,
+                                   void *out_host, int64_t out_capacity_frames)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_submit: NULL chain");
+    if (c->slots_busy >= 2) return fail(PB_ERR_STATE, "pb_chain_submit: pipeline full, collect first");
+    if (!buf_frames || n_buffers < 1) return fail(PB_ERR_INVALID, "pb_chain_submit: need at least one buffer");
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    Slot &sl = c->slots[c->slot_head];
+    int32_t r = ensure_slot(c, sl);
+    if (r != PB_OK) return r;
+    int64_t tin = 0;
+    for (int i = 0; i < n_buffers; i++) tin += buf_frames[i] > 0 ? buf_frames[i] : 0;
+    if (tin > c->max_frames) return fail(PB_ERR_CAPACITY, "pb_chain_submit: %lld frames > buffer_frames*max_batch", (long long)tin);
+    const size_t in_bytes = c->elem * (size_t)tin * c->C;
+    if (tin > 0 && (!in_host || !out_host)) return fail(PB_ERR_INVALID, "pb_chain_submit: NULL buffer");
+    // H2D: pinned caller memory goes direct, pageable memory (the Go heap) is
+    // staged first so that no caller pointer outlives this call.
+    if (in_bytes) {
+        const void *src = in_host;
+        if (!is_pinned(in_host)) {
+            if (!sl.h_in) PB_CUDA(cudaMallocHost(&sl.h_in, c->elem * (size_t)c->max_frames * c->C));
+            memcpy(sl.h_in, in_host, in_bytes);
+            src = sl.h_in;
+        }
+        PB_CUDA(cudaMemcpyAsync(sl.d_in, src, in_bytes, cudaMemcpyHostToDevice, c->st_h2d));
+    }
+    PB_CUDA(cudaEventRecord(sl.ev_h2d, c->st_h2d));
+    PB_CUDA(cudaStreamWaitEvent(c->st_compute, sl.ev_h2d, 0));
+    // the slot's previous D2H must have drained before d_out is overwritten
+    PB_CUDA(cudaStreamWaitEvent(c->st_compute, sl.ev_d2h, 0));
+    sl.out_counts.assign((size_t)n_buffers, 0);
+    r = run_batch_device(c, sl.d_in, buf_frames, n_buffers, sl.d_out, c->max_frames, sl.out_counts.data(), c->st_compute);
+    if (r != PB_OK) return r;
+    int64_t tout = 0;
+    for (auto v : sl.out_counts) tout += v;
+    if (tout > out_capacity_frames) return fail(PB_ERR_CAPACITY, "pb_chain_submit: output needs %lld frames", (long long)tout);
+    PB_CUDA(cudaEventRecord(sl.ev_done, c->st_compute));
+    PB_CUDA(cudaStreamWaitEvent(c->st_d2h, sl.ev_done, 0));
+    sl.out_frames = tout;
+    sl.user_out = nullptr;
+    const size_t out_bytes = c->elem * (size_t)tout * c->C;
+    if (out_bytes) {
+        void *dst = out_host;
+        if (!is_pinned(out_host)) {
+            if (!sl.h_out) PB_CUDA(cudaMallocHost(&sl.h_out, c->elem * (size_t)c->max_frames * c->C));
+            dst = sl.h_out;
+            sl.user_out = out_host;
+        }
+        PB_CUDA(cudaMemcpyAsync(dst, sl.d_out, out_bytes, cudaMemcpyDeviceToHost, c->st_d2h));
+    }
+    PB_CUDA(cudaEventRecord(sl.ev_d2h, c->st_d2h));
+    sl.busy = true;
+    c->slot_head ^= 1;
+    c->slots_busy++;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_collect(pb_chain *c, int64_t *buf_out_frames, int32_t n_buffers)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_collect: NULL chain");
+    if (c->slots_busy < 1) return fail(PB_ERR_STATE, "pb_chain_collect: nothing submitted");
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    Slot &sl = c->slots[c->slot_tail];
+    if (n_buffers != (int)sl.out_counts.size()) return fail(PB_ERR_INVALID, "pb_chain_collect: batch had %zu buffers", sl.out_counts.size());
+    PB_CUDA(cudaEventSynchronize(sl.ev_d2h));
+    {
+        int flag = 0;
+        PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) return fail(PB_ERR_CUDA, "fused tile kernel: look-back wait timed out (kernel error flag set)");
+    }
+    if (sl.user_out && sl.out_frames) memcpy(sl.user_out, sl.h_out, c->elem * (size_t)sl.out_frames * c->C);
+    if (buf_out_frames)
+        for (int i = 0; i < n_buffers; i++) buf_out_frames[i] = sl.out_counts[(size_t)i];
+    sl.busy = false;
+    sl.user_out = nullptr;
+    c->slot_tail ^= 1;
+    c->slots_busy--;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_process(pb_chain *c, const void *in_host, int64_t in_frames, void *out_host,
+                                    int64_t out_capacity_frames, int64_t *out_frames)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_process: NULL chain");
+    if (c->slots_busy) return fail(PB_ERR_STATE, "pb_chain_process while submitted batches are in flight");
+    // A single call may carry up to max_batch buffers' worth of frames.
+    if (in_frames < 0 || in_frames > c->max_frames) return fail(PB_ERR_INVALID, "pb_chain_process: %lld frames", (long long)in_frames);
+    std::vector<int64_t> bf;
+    int64_t left = in_frames;
+    do {
+        const int64_t n = left < c->buffer_frames ? left : c->buffer_frames;
+        bf.push_back(n);
+        left -= n;
+    } while (left > 0);
+    int32_t r = pb_chain_submit(c, in_host, bf.data(), (int32_t)bf.size(), out_host, out_capacity_frames);
+    if (r != PB_OK) return r;
+    std::vector<int64_t> oc(bf.size());
+    r = pb_chain_collect(c, oc.data(), (int32_t)oc.size());
+    if (r != PB_OK) return r;
+    int64_t tot = 0;
+    for (auto v : oc) tot += v;
+    if (out_frames) *out_frames = tot;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_set_stage(pb_chain *c, int32_t idx, const pb_stage_desc *st)
+{
+    if (!c || !st) return fail(PB_ERR_INVALID, "pb_chain_set_stage: NULL argument");
+    if (idx < 0 || idx >= (int)c->stages.size()) return fail(PB_ERR_INVALID, "pb_chain_set_stage: stage %d of %zu", idx, c->stages.size());
+    if (c->slots_busy) return fail(PB_ERR_STATE, "pb_chain_set_stage while submitted batches are in flight");
+    StageCopy &cur = c->stages[(size_t)idx];
+    if (st->kind != cur.d.kind) return fail(PB_ERR_INVALID, "pb_chain_set_stage: kind may not change");
+    int32_t r = validate_stage(*st, idx);
+    if (r != PB_OK) return r;
+    if ((st->kind == PB_STAGE_FIR || st->kind == PB_STAGE_RESAMPLE) &&
+        (st->n_taps != cur.d.n_taps || st->up != cur.d.up || st->down != cur.d.down))
+        return fail(PB_ERR_INVALID, "pb_chain_set_stage: n_taps/up/down may not change");
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    // mutations land between buffers (pipe.go:433): drain what is in flight first
+    PB_CUDA(cudaDeviceSynchronize());
+    cur.d = *st;
+    if (st->taps && st->n_taps > 0) cur.taps.assign(st->taps, st->taps + st->n_taps);
+    cur.d.taps = nullptr;
+    for (auto &s : c->segs) {
+        bool mine = s.fir_stage == idx || s.bq_stage == idx || s.rs_stage == idx;
+        for (auto &gs : s.gain_stages) mine = mine || gs.first == idx;
+        if (mine) return refresh_segment_params(c, s);
+    }
+    return PB_OK;  // a COPY stage: nothing to update
+}
+
+extern "C" int32_t pb_chain_meter_read(pb_chain *c, double *peak, double *sumsq, int64_t *frames)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_meter_read: NULL chain");
+    if (!c->d_meter) return fail(PB_ERR_STATE, "pb_chain_meter_read: chain was created without PB_CHAIN_METER");
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaDeviceSynchronize());
+    if (peak) PB_CUDA(cudaMemcpy(peak, c->d_meter, sizeof(double) * (size_t)c->C, cudaMemcpyDeviceToHost));
+    if (sumsq) PB_CUDA(cudaMemcpy(sumsq, c->d_meter + c->C, sizeof(double) * (size_t)c->C, cudaMemcpyDeviceToHost));
+    if (frames) *frames = c->meter_frames;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_chain_last_path(const pb_chain *c, int32_t *path, int64_t *kernel_launches)
+{
+    if (!c) return fail(PB_ERR_INVALID, "pb_chain_last_path: NULL chain");
+    if (path) *path = c->last_path;
+    if (kernel_launches) *kernel_launches = c->launches;
+    return PB_OK;
+}
+
+// ---- memory helpers ------------------------------------------------------------
+
+extern "C" int32_t pb_device_count(int32_t *count)
+{
+    if (!count) return fail(PB_ERR_INVALID, "pb_device_count: NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(PB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return PB_OK;
+}
+
+extern "C" int32_t pb_device_alloc(int32_t device, int64_t bytes, void **ptr)
+{
+    if (!ptr || bytes < 0) return fail(PB_ERR_INVALID, "pb_device_alloc: bad argument");
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaMalloc(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_device_free(int32_t device, void *ptr)
+{
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaFree(ptr));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_host_alloc_pinned(int64_t bytes, void **ptr)
+{
+    if (!ptr || bytes < 0) return fail(PB_ERR_INVALID, "pb_host_alloc_pinned: bad argument");
+    PB_CUDA(cudaMallocHost(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_host_free_pinned(void *ptr)
+{
+    PB_CUDA(cudaFreeHost(ptr));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_memcpy_h2d(int32_t device, void *dst, const void *src, int64_t bytes)
+{
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_memcpy_d2h(int32_t device, void *dst, const void *src, int64_t bytes)
+{
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_device_synchronize(int32_t device)
+{
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaDeviceSynchronize());
+    return PB_OK;
+}
+
+extern "C" int32_t pb_ipc_export(int32_t device, void *ptr, uint8_t handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    if (!ptr || !handle) return fail(PB_ERR_INVALID, "pb_ipc_export: NULL");
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    cudaIpcMemHandle_t h;
+    PB_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    return PB_OK;
+}
+
+extern "C" int32_t pb_ipc_open(int32_t device, const uint8_t handle[64], void **ptr)
+{
+    if (!ptr || !handle) return fail(PB_ERR_INVALID, "pb_ipc_open: NULL");
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    PB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PB_OK;
+}
+
+extern "C" int32_t pb_ipc_close(int32_t device, void *ptr)
+{
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return PB_OK;
+}

@@ -1,0 +1,326 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (pipe_b200.abi ->
+libpipe_b200.so), against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star / SURVEY.md H2):
+  * integer bookkeeping (frames per buffer, message counts): bit-exact;
+  * float32 path vs the float64 oracle: max|y - ref| <= 1e-6 * max|ref| per
+    channel per buffer (REL_F32 below);
+  * float64 path vs the float64 oracle: 1e-12 on the same measure.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as orc
+from pipe_b200 import abi, design
+
+pytestmark = pytest.mark.gpu
+
+REL_F32 = 1e-6
+REL_F64 = 1e-12
+
+
+def assert_parity(y, ref, rel, what=""):
+    assert y.shape == ref.shape, f"{what}: shape {y.shape} vs {ref.shape}"
+    if ref.size == 0:
+        return
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = np.abs(ref).max(axis=0)
+    err = np.abs(np.asarray(y, dtype=np.float64) - ref).max(axis=0)
+    bad = err > rel * scale + 1e-300
+    assert not bad.any(), (f"{what}: worst channel {int(np.argmax(err / (scale + 1e-300)))} "
+                           f"err {err.max():.3e} vs scale {scale[np.argmax(err)]:.3e} "
+                           f"(ratio {np.max(err / (scale + 1e-300)):.3e}, allowed {rel:.1e})")
+
+
+def signal_input(frames, channels, seed=0, line=0):
+    x = orc.source_fill(seed * 7919, frames * channels, seed=1234, line=line)
+    return x.reshape(frames, channels)
+
+
+def run_both(stages, channels, sizes, dtype=np.float32, buffer_frames=None, seed=0, rel=None, max_batch=1):
+    rel = rel if rel is not None else (REL_F32 if dtype == np.float32 else REL_F64)
+    bf = buffer_frames or max(max(sizes), 1)
+    gpu = abi.Chain(channels, stages, buffer_frames=bf, dtype=dtype, max_batch=max_batch)
+    cpu = orc.Chain(channels, stages)
+    x = signal_input(sum(sizes), channels, seed)
+    pos = 0
+    for i, n in enumerate(sizes):
+        blk = x[pos:pos + n]
+        pos += n
+        ref = cpu.process(blk)
+        assert gpu.peek_out_frames(n) == len(ref)
+        y = gpu.process(blk.astype(dtype))
+        assert len(y) == len(ref), f"buffer {i}: frames {len(y)} vs {len(ref)}"  # bit-exact bookkeeping
+        assert_parity(y, ref, rel, f"buffer {i} ({n} frames)")
+    gpu.close()
+
+
+# ------------------------------------------------------------------ configs --
+
+def test_config1_passthrough_f64_is_bit_exact():
+    # configs[0]: mock.Processor pass-through, 2 ch float64, 512-frame buffers
+    gpu = abi.Chain(2, [{"kind": "copy"}], buffer_frames=512, dtype=np.float64)
+    x = signal_input(512 * 3 + 17, 2)
+    for i in range(0, len(x), 512):
+        blk = x[i:i + 512]
+        assert np.array_equal(gpu.process(blk), blk)
+    # the reference's own value goldens (mock_test.go:133-146)
+    for vals in ([1, 1, 1, 1], [1, 1, 1, 1, 2, 2, 2, 2]):
+        g1 = abi.Chain(1, [{"kind": "copy"}], buffer_frames=8, dtype=np.float64)
+        v = np.asarray(vals, dtype=np.float64).reshape(-1, 1)
+        assert np.array_equal(g1.process(v), v)
+
+
+def test_config2_gain_biquad_64ch_4096():
+    run_both(design.config_stages("gain_biquad"), 64, [4096] * 4)
+
+
+def test_config3_chain4_small_channels():
+    run_both(design.config_stages("chain4"), 8, [1024] * 6)
+
+
+def test_config3_chain4_1024ch_4096_counts_and_values():
+    stages = design.config_stages("chain4")
+    gpu = abi.Chain(1024, stages, buffer_frames=4096)
+    cpu = orc.Chain(1024, stages)
+    counts = []
+    for b in range(2):
+        x = signal_input(4096, 1024, seed=b + 1)
+        ref = cpu.process(x, threads=os.cpu_count() or 1)
+        y = gpu.process(x.astype(np.float32))
+        counts.append(len(y))
+        assert_parity(y, ref, REL_F32, f"buffer {b}")
+    assert counts == [3763, 3763]
+
+
+def test_resampler_frame_sequence_bit_exact():
+    # 4096-frame buffers -> 3763,3763,3763,3763,3764 repeating
+    stages = [design.config_stages("chain4")[3]]
+    gpu = abi.Chain(4, stages, buffer_frames=4096)
+    seq = [len(gpu.process(np.zeros((4096, 4), np.float32))) for _ in range(10)]
+    assert seq == [3763, 3763, 3763, 3763, 3764] * 2
+
+
+# --------------------------------------------------------------- edge cases --
+
+@pytest.mark.parametrize("channels", [1, 3, 33, 100])
+def test_odd_channel_counts(channels):
+    run_both(design.config_stages("chain4"), channels, [700, 300])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_ragged_buffer_sizes_carry_state(dtype):
+    sizes = [1, 7, 255, 256, 257, 1000, 0, 3, 15, 16, 17, 2048]
+    run_both(design.config_stages("chain4"), 5, sizes, dtype=dtype, buffer_frames=2048)
+
+
+def test_short_final_buffer_like_pipe_test():
+    # pipe_test.go:337: Limit 1040 with bufferSize 512 -> 512, 512, 16
+    run_both(design.config_stages("gain_biquad"), 1, [512, 512, 16], buffer_frames=512)
+
+
+def test_empty_buffer_is_a_no_op():
+    gpu = abi.Chain(2, design.config_stages("chain4"), buffer_frames=64)
+    assert gpu.process(np.zeros((0, 2), np.float32)).shape == (0, 2)
+
+
+@pytest.mark.parametrize("n_taps", [1, 2, 16, 33, 257, 600])
+def test_fir_lengths(n_taps):
+    taps = design.lowpass_fir(n_taps, 0.2) if n_taps > 2 else np.array([0.75, -0.25][:n_taps])
+    run_both([{"kind": "fir", "taps": taps}], 6, [500, 500, 41])
+
+
+def test_fir_impulse_returns_taps():
+    taps = design.lowpass_fir(257, 20000 / 48000)
+    gpu = abi.Chain(2, [{"kind": "fir", "taps": taps}], buffer_frames=600, dtype=np.float64)
+    x = np.zeros((600, 2))
+    x[0, 0] = 1.0
+    y = gpu.process(x)
+    assert np.array_equal(y[:257, 0], taps)
+    assert not y[:, 1].any()
+
+
+@pytest.mark.parametrize("kind,f0,q", [("lowpass", 8000.0, 0.9), ("highpass", 200.0, 0.707), ("peaking", 1000.0, 4.0)])
+def test_biquad_kinds(kind, f0, q):
+    b, a = design.biquad(kind, f0, 48000.0, q=q, gain_db=6.0)
+    run_both([{"kind": "biquad", "b": b, "a": a}], 40, [4096, 4096, 100])
+
+
+@pytest.mark.parametrize("up,down,tpp", [(147, 160, 16), (1, 2, 8), (2, 3, 12), (1, 1, 4), (147, 160, 32)])
+def test_resampler_ratios(up, down, tpp):
+    proto = design.resampler_prototype(up, down, tpp)
+    run_both([{"kind": "resample", "up": up, "down": down, "taps": proto}], 7, [1000, 1, 159, 160, 1680])
+
+
+def test_multi_segment_chains():
+    b1, a1 = design.biquad("lowpass", 6000.0, 48000.0, q=0.8)
+    b2, a2 = design.biquad("highpass", 300.0, 48000.0, q=0.7)
+    proto = design.resampler_prototype(1, 2, 8)
+    stages = [
+        {"kind": "biquad", "b": b1, "a": a1}, {"kind": "gain", "gain": 1.5},
+        {"kind": "biquad", "b": b2, "a": a2},                       # second biquad -> second segment
+        {"kind": "resample", "up": 1, "down": 2, "taps": proto},
+        {"kind": "fir", "taps": design.lowpass_fir(31, 0.2)},       # FIR after resample -> third segment
+        {"kind": "copy"}, {"kind": "gain", "gain": -0.5},
+    ]
+    run_both(stages, 9, [999, 1000, 1, 500], buffer_frames=1000)
+
+
+def test_batched_launch_equals_per_buffer_launches():
+    stages = design.config_stages("chain4")
+    ch, bf, nb = 64, 1024, 5
+    x = signal_input(bf * nb - 100, ch).astype(np.float32)   # last buffer short
+    sizes = [bf] * (nb - 1) + [bf - 100]
+    cpu = orc.Chain(ch, stages)
+    refs = [cpu.process(x[i * bf:i * bf + n]) for i, n in enumerate(sizes)]
+    gpu = abi.Chain(ch, stages, buffer_frames=bf, max_batch=nb)
+    d_in, d_out = abi.DeviceBuffer(x.nbytes), abi.DeviceBuffer(x.nbytes)
+    d_in.upload(x)
+    counts = gpu.process_batch_device(d_in.ptr, sizes, d_out.ptr, len(x))
+    gpu.sync()
+    assert counts == [len(r) for r in refs]
+    y = d_out.download((sum(counts), ch), np.float32)
+    pos = 0
+    for i, r in enumerate(refs):
+        assert_parity(y[pos:pos + len(r)], r, REL_F32, f"batched buffer {i}")
+        pos += len(r)
+    assert gpu.last_path()[0] in (1, 2)
+
+
+def test_reset_restarts_the_stream():
+    stages = design.config_stages("chain4")
+    gpu = abi.Chain(4, stages, buffer_frames=512)
+    x = signal_input(512, 4).astype(np.float32)
+    y0 = gpu.process(x)
+    gpu.process(x)
+    gpu.reset()
+    assert np.array_equal(gpu.process(x), y0)
+
+
+def test_mutations_between_buffers():
+    # pipe.go:433: parameter changes land between buffers, state is kept
+    b, a = design.biquad("lowpass", 8000.0, 48000.0, q=0.9)
+    b2, a2 = design.biquad("lowpass", 2000.0, 48000.0, q=0.7)
+    proto = design.resampler_prototype(2, 3, 12)
+    stages = [{"kind": "gain", "gain": 1.0}, {"kind": "fir", "taps": design.lowpass_fir(65, 0.3)},
+              {"kind": "biquad", "b": b, "a": a}, {"kind": "gain", "gain": 1.0},
+              {"kind": "resample", "up": 2, "down": 3, "taps": proto}]
+    gpu, cpu = abi.Chain(3, stages, buffer_frames=300), orc.Chain(3, stages)
+    x = signal_input(1200, 3)
+    edits = {1: (0, {"kind": "gain", "gain": 2.0}), 2: (2, {"kind": "biquad", "b": b2, "a": a2}),
+             3: (3, {"kind": "gain", "gain": 0.25})}
+    for i in range(4):
+        if i in edits:
+            gpu.set_stage(*edits[i])
+            cpu.set_stage(*edits[i])
+        blk = x[i * 300:(i + 1) * 300]
+        assert_parity(gpu.process(blk.astype(np.float32)), cpu.process(blk), REL_F32, f"buffer {i}")
+
+
+def test_fused_meter_sink_and_standalone_meter():
+    stages = design.config_stages("gain_biquad")
+    gpu = abi.Chain(40, stages, buffer_frames=1000, flags=abi.CHAIN_METER)
+    cpu = orc.Chain(40, stages)
+    x = signal_input(3000, 40)
+    refs = np.concatenate([cpu.process(x[i:i + 1000]) for i in range(0, 3000, 1000)])
+    ys = np.concatenate([gpu.process(x[i:i + 1000].astype(np.float32)) for i in range(0, 3000, 1000)])
+    peak, sumsq, frames = gpu.meter_read()
+    rp, rs = orc.meter(refs)
+    assert frames == 3000
+    np.testing.assert_allclose(peak, rp, rtol=2e-6)
+    np.testing.assert_allclose(sumsq, rs, rtol=2e-6)
+    # stand-alone meter kernel on the GPU output: exact peak, double-accumulated sum of squares
+    d = abi.DeviceBuffer(ys.nbytes)
+    d.upload(ys)
+    acc = abi.DeviceBuffer(2 * 40 * 8)
+    acc.upload(np.zeros(80))
+    abi.meter_device(d.ptr, abi.PB_F32, 3000, 40, acc.ptr, acc.ptr + 40 * 8)
+    got = acc.download((2, 40), np.float64)
+    p2, s2 = orc.meter(ys.astype(np.float64))
+    assert np.array_equal(got[0], p2)
+    np.testing.assert_allclose(got[1], s2, rtol=1e-12)
+
+
+def test_source_fill_matches_oracle_bit_exact():
+    for dtype, pb in ((np.float32, abi.PB_F32), (np.float64, abi.PB_F64)):
+        n = 100003
+        d = abi.DeviceBuffer(n * np.dtype(dtype).itemsize)
+        abi.source_fill(d.ptr, pb, 12345, n, seed=1234, line=3)
+        got = d.download((n,), dtype)
+        assert np.array_equal(got.astype(np.float64), orc.source_fill(12345, n, seed=1234, line=3))
+
+
+def test_mix_sum_fan_in_bit_exact():
+    # configs[4] in miniature on one device: 4 Lines x 256 ch, fan-in sum
+    n = 256 * 1000
+    ins = [signal_input(1000, 256, seed=i, line=i).astype(np.float32) for i in range(4)]
+    bufs = []
+    for a in ins:
+        d = abi.DeviceBuffer(a.nbytes)
+        d.upload(a)
+        bufs.append(d)
+    out = abi.DeviceBuffer(ins[0].nbytes)
+    abi.mix_sum([b.ptr for b in bufs], abi.PB_F32, n, out.ptr)
+    got = out.download((1000, 256), np.float32)
+    ref = ((ins[0] + ins[1]) + ins[2]) + ins[3]          # float32, same order
+    assert np.array_equal(got, ref)
+    assert_parity(got, orc.mix_sum([a.astype(np.float64) for a in ins]), REL_F32)
+
+
+def test_pipelined_submit_collect_with_pinned_buffers():
+    stages = design.config_stages("chain4")
+    ch, bf, nb, steps = 32, 512, 4, 5
+    gpu = abi.Chain(ch, stages, buffer_frames=bf, max_batch=nb)
+    cpu = orc.Chain(ch, stages)
+    nbytes = bf * nb * ch * 4
+    pin_in = [abi.PinnedBuffer(nbytes) for _ in range(2)]
+    pin_out = [abi.PinnedBuffer(nbytes) for _ in range(2)]
+    xs = [signal_input(bf * nb, ch, seed=s) for s in range(steps)]
+    refs = [cpu.process(x) for x in xs]
+    got = []
+    for s in range(steps + 1):
+        if s < steps:
+            pin_in[s & 1].array((bf * nb, ch), np.float32)[:] = xs[s]
+            gpu.submit(pin_in[s & 1].ptr, [bf] * nb, pin_out[s & 1].ptr, bf * nb)
+        if s >= 1:
+            counts = gpu.collect(nb)
+            got.append(pin_out[(s - 1) & 1].array((bf * nb, ch), np.float32)[:sum(counts)].copy())
+    for s in range(steps):
+        assert_parity(got[s], refs[s], REL_F32, f"step {s}")
+
+
+def test_golden_fixtures_from_scipy():
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "dsp_golden.npz"))
+    for case, cfg, ch, bf in (("a", "gain_biquad", 8, 256), ("b", "chain4", 4, 640)):
+        gpu = abi.Chain(ch, design.config_stages(cfg), buffer_frames=bf)
+        x = G[f"{case}_x"]
+        y = np.concatenate([gpu.process(x[i:i + bf]) for i in range(0, len(x), bf)])
+        ref = G[f"{case}_y"]
+        for i in range(0, len(ref), max(1, len(ref) // 3)):
+            assert_parity(y[i:i + len(ref) // 3], ref[i:i + len(ref) // 3], REL_F32, f"golden {case}")
+    gpu = abi.Chain(2, [design.config_stages("chain4")[1]], buffer_frames=300)
+    y = np.concatenate([gpu.process(G["c_x"][i:i + 300]) for i in range(0, 1024, 300)])
+    assert_parity(y, G["c_y"], REL_F32, "golden c")
+
+
+# -------------------------------------------------------------------- errors --
+
+def test_error_behaviour():
+    with pytest.raises(abi.PipeB200Error) as e:
+        abi.Chain(1, [{"kind": "resample", "up": 3, "down": 2, "taps": np.ones(6)}], buffer_frames=16)
+    assert e.value.code == abi.PB_ERR_UNSUPPORTED
+    with pytest.raises(abi.PipeB200Error) as e:
+        abi.Chain(0, [{"kind": "copy"}], buffer_frames=16)
+    assert e.value.code == abi.PB_ERR_INVALID
+    gpu = abi.Chain(1, [{"kind": "copy"}], buffer_frames=16)
+    with pytest.raises(abi.PipeB200Error) as e:
+        gpu.process(np.zeros((17, 1), np.float32))          # more frames than bufferSize*max_batch
+    assert e.value.code == abi.PB_ERR_INVALID
+    with pytest.raises(abi.PipeB200Error) as e:
+        gpu.collect(1)                                       # collect without submit
+    assert e.value.code == abi.PB_ERR_STATE
+    with pytest.raises(abi.PipeB200Error) as e:
+        gpu.set_stage(0, {"kind": "gain", "gain": 2.0})      # kind may not change
+    assert e.value.code == abi.PB_ERR_INVALID
