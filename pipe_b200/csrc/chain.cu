@@ -163,7 +163,11 @@ static int32_t configure_kernel(pb_chain *c, Segment &s)
 {
     auto kern = chain_tile_kernel<T, FB>;
     // the attribute is per function, not per chain: always raise it to the architectural maximum
-    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    cudaFuncAttributes fa{};
+    PB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const int max_dyn = 232448 - (int)fa.sharedSizeBytes;  // 227 KB per CTA, static part included
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    if ((int)s.smem > max_dyn) return fail(PB_ERR_UNSUPPORTED, "tile needs %zu B of shared memory (max %d)", s.smem, max_dyn);
     int per_sm = 0;
     PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, s.smem));
     if (per_sm < 1) return fail(PB_ERR_UNSUPPORTED, "fused tile kernel does not fit on an SM (%zu B shared)", s.smem);
@@ -201,8 +205,8 @@ static int32_t refresh_segment_params(pb_chain *c, Segment &s)
                                  M[2] * A[0] + M[3] * A[2], M[2] * A[1] + M[3] * A[3]};
             for (int i = 0; i < 4; i++) M[i] = N[i];
         }
-        PB_CUDA(upload_any(c->dtype, s.d_apow, apow));
-        PB_CUDA(upload_any(c->dtype, s.d_wt, wt));
+        PB_CUDA(upload<double>(s.d_apow, apow));
+        PB_CUDA(upload<double>(s.d_wt, wt));
     }
     if (s.rs_stage >= 0) {
         const auto &st = c->stages[s.rs_stage];
@@ -249,7 +253,7 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     s.wt_len = (s.L + s.Hr) / kNW + 2;
     s.apow_len = s.L + s.Hr + 1;
     s.smem = smem_for(s.L);
-    if (s.smem > 227 * 1024)
+    if (s.smem > 226 * 1024)
         return fail(PB_ERR_UNSUPPORTED, "FIR with %d taps needs %zu B of shared memory per tile (max 232448)", s.Hf + 1, s.smem);
     if (f32) {
         int32_t r = configure_kernel<float, 16>(c, s);
@@ -261,12 +265,12 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     // tables
     if (has_fir) PB_CUDA(cudaMalloc(&s.d_taps, el * (size_t)s.tp_len));
     if (s.bq_stage >= 0) {
-        PB_CUDA(cudaMalloc(&s.d_apow, el * (size_t)s.apow_len * 4));
-        PB_CUDA(cudaMalloc(&s.d_wt, el * (size_t)s.wt_len * 2));
+        PB_CUDA(cudaMalloc(&s.d_apow, sizeof(double) * (size_t)s.apow_len * 4));
+        PB_CUDA(cudaMalloc(&s.d_wt, sizeof(double) * (size_t)s.wt_len * 2));
         s.lb_tiles = (int)ceil_div64(c->max_frames, s.L) + 1;
         const size_t groups = (size_t)(c->C + kCg - 1) / kCg;
-        PB_CUDA(cudaMalloc(&s.d_agg, el * groups * s.lb_tiles * 64));
-        PB_CUDA(cudaMalloc(&s.d_inc, el * groups * s.lb_tiles * 64));
+        PB_CUDA(cudaMalloc(&s.d_agg, sizeof(double) * groups * s.lb_tiles * 64));
+        PB_CUDA(cudaMalloc(&s.d_inc, sizeof(double) * groups * s.lb_tiles * 64));
         PB_CUDA(cudaMalloc((void **)&s.d_status, sizeof(unsigned) * groups * s.lb_tiles));
         PB_CUDA(cudaMemset(s.d_status, 0, sizeof(unsigned) * groups * s.lb_tiles));
     }
@@ -281,8 +285,8 @@ static int32_t build_segment(pb_chain *c, Segment &s)
             PB_CUDA(cudaMemset(s.d_yhist[i], 0, el * (size_t)s.Hr * c->C));
         }
         if (s.bq_stage >= 0) {
-            PB_CUDA(cudaMalloc(&s.d_state[i], el * (size_t)c->C * 2));
-            PB_CUDA(cudaMemset(s.d_state[i], 0, el * (size_t)c->C * 2));
+            PB_CUDA(cudaMalloc(&s.d_state[i], sizeof(double) * (size_t)c->C * 2));
+            PB_CUDA(cudaMemset(s.d_state[i], 0, sizeof(double) * (size_t)c->C * 2));
         }
     }
     return refresh_segment_params(c, s);
@@ -294,7 +298,7 @@ static int32_t reset_segment(pb_chain *c, Segment &s)
     for (int i = 0; i < 2; i++) {
         if (s.d_xhist[i]) PB_CUDA(cudaMemsetAsync(s.d_xhist[i], 0, el * (size_t)s.Hf * c->C, c->st_compute));
         if (s.d_yhist[i]) PB_CUDA(cudaMemsetAsync(s.d_yhist[i], 0, el * (size_t)s.Hr * c->C, c->st_compute));
-        if (s.d_state[i]) PB_CUDA(cudaMemsetAsync(s.d_state[i], 0, el * (size_t)c->C * 2, c->st_compute));
+        if (s.d_state[i]) PB_CUDA(cudaMemsetAsync(s.d_state[i], 0, sizeof(double) * (size_t)c->C * 2, c->st_compute));
     }
     s.acc = 0;
     return PB_OK;
@@ -328,14 +332,14 @@ static int32_t launch_segment(pb_chain *c, Segment &s, const void *in, int64_t n
     p.xhist = (const T *)s.d_xhist[s.pp];
     p.xhist_next = (T *)s.d_xhist[s.pp ^ 1];
     p.has_bq = has_bq;
-    p.b0 = (T)s.b[0]; p.b1 = (T)s.b[1]; p.b2 = (T)s.b[2]; p.a1 = (T)s.a[0]; p.a2 = (T)s.a[1];
-    p.bq_wt = (const T *)s.d_wt;
-    p.bq_apow = (const T *)s.d_apow;
+    p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
+    p.bq_wt = (const double *)s.d_wt;
+    p.bq_apow = (const double *)s.d_apow;
     p.wt_len = s.wt_len;
-    p.bq_state = (const T *)s.d_state[s.pp];
-    p.bq_state_next = (T *)s.d_state[s.pp ^ 1];
-    p.lb_agg = (T *)s.d_agg;
-    p.lb_inc = (T *)s.d_inc;
+    p.bq_state = (const double *)s.d_state[s.pp];
+    p.bq_state_next = (double *)s.d_state[s.pp ^ 1];
+    p.lb_agg = (double *)s.d_agg;
+    p.lb_inc = (double *)s.d_inc;
     p.lb_status = s.d_status;
     c->epoch = (c->epoch % 0x3ffffffeu) + 1u;
     p.epoch = c->epoch;

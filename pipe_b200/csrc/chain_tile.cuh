@@ -55,14 +55,16 @@ struct TileParams {
     T *xhist_next;
     // biquad
     int has_bq;
-    T b0, b1, b2, a1, a2;
-    const T *bq_wt;       // [wt_len][2]  Wt[k] = A^k B
-    const T *bq_apow;     // [L+Hr+1][4]  A^k row-major
+    // The recursion runs in double whatever T is: an fp32 TDF-II with poles near z = 1 has a
+    // rounding-noise gain far above the 1e-6 parity bar, and 7 DFMA/sample is cheap next to the FIR.
+    double b0, b1, b2, a1, a2;
+    const double *bq_wt;     // [wt_len][2]  Wt[k] = A^k B
+    const double *bq_apow;   // [L+Hr+1][4]  A^k row-major
     int wt_len;
-    const T *bq_state;    // [C][2] state at the first frame of this call
-    T *bq_state_next;     // [C][2] state after the last frame of this call
-    T *lb_agg;            // [n_groups][n_tiles][32][2]
-    T *lb_inc;
+    const double *bq_state;  // [C][2] state at the first frame of this call
+    double *bq_state_next;   // [C][2] state after the last frame of this call
+    double *lb_agg;          // [n_groups][n_tiles][32][2]
+    double *lb_inc;
     unsigned *lb_status;  // [n_groups][n_tiles]
     unsigned epoch;
     // resample
@@ -81,11 +83,10 @@ struct TileParams {
     int vec_ok;           // float4 path usable (f32, C%4==0, 16B-aligned pointers)
 };
 
-template <typename T>
-__device__ __forceinline__ void mat2_apply(const T *__restrict__ m, T &v0, T &v1)
+__device__ __forceinline__ void mat2_apply(const double *__restrict__ m, double &v0, double &v1)
 {
-    const T r0 = m[0] * v0 + m[1] * v1;
-    const T r1 = m[2] * v0 + m[3] * v1;
+    const double r0 = m[0] * v0 + m[1] * v1;
+    const double r1 = m[2] * v0 + m[3] * v1;
     v0 = r0;
     v1 = r1;
 }
@@ -100,12 +101,12 @@ struct TileSmem {
         rowsB_alloc = L + Hr + FB;               // partial FIR blocks write nothing past rowsB but index math stays in range
         rowsA_alloc = L + Hr + Hf + 2 * FB;      // FIR chunking reads up to 2*FB-1 zeroed rows past the tile
         size_t o = 0;
-        off_tp = o;   o += sizeof(T) * (size_t)((tp_len + 3) & ~3);
-        off_wt = o;   o += sizeof(T) * (size_t)((2 * wt_len + 3) & ~3);
-        off_zq = o;   o += sizeof(T) * kNW * kCg * 2;
-        off_sin = o;  o += sizeof(T) * kNW * kCg * 2;
-        o = (o + 15) & ~(size_t)15;
+        off_wt = o;   o += sizeof(double) * (size_t)((2 * wt_len + 1) & ~1);
+        off_zq = o;   o += sizeof(double) * kNW * kCg * 2;
+        off_sin = o;  o += sizeof(double) * kNW * kCg * 2;
         off_red = o;  o += sizeof(double) * kNW * kCg * 2;
+        off_tp = o;   o += sizeof(T) * (size_t)((tp_len + 3) & ~3);
+        o = (o + 15) & ~(size_t)15;
         off_bufA = o; o += sizeof(T) * (size_t)rowsA_alloc * kCg;
         off_bufB = o; o += has_fir ? sizeof(T) * (size_t)rowsB_alloc * kCg : 0;
         total = o;
@@ -120,9 +121,9 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
 
     const TileSmem<T> lay(p.L, p.Hf, p.Hr, p.has_fir, p.tp_len, p.wt_len, FB);
     T *tp_s = reinterpret_cast<T *>(smem_raw + lay.off_tp);
-    T *wt_s = reinterpret_cast<T *>(smem_raw + lay.off_wt);
-    T *zq_s = reinterpret_cast<T *>(smem_raw + lay.off_zq);
-    T *sin_s = reinterpret_cast<T *>(smem_raw + lay.off_sin);
+    double *wt_s = reinterpret_cast<double *>(smem_raw + lay.off_wt);
+    double *zq_s = reinterpret_cast<double *>(smem_raw + lay.off_zq);
+    double *sin_s = reinterpret_cast<double *>(smem_raw + lay.off_sin);
     double *red_s = reinterpret_cast<double *>(smem_raw + lay.off_red);
     T *bufA = reinterpret_cast<T *>(smem_raw + lay.off_bufA);
     T *bufB = p.has_fir ? reinterpret_cast<T *>(smem_raw + lay.off_bufB) : bufA;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
 
     // per-launch constants into shared memory
     for (int i = tid; i < p.tp_len; i += kTileThreads) tp_s[i] = p.has_fir ? p.taps_padded[i] : T(0);
-    for (int i = tid; i < 2 * p.wt_len; i += kTileThreads) wt_s[i] = p.has_bq ? p.bq_wt[i] : T(0);
+    for (int i = tid; i < 2 * p.wt_len; i += kTileThreads) wt_s[i] = p.has_bq ? p.bq_wt[i] : 0.0;
 
     for (;;) {
         __syncthreads();  // previous tile fully done with shared memory (and constants visible)
@@ -205,11 +206,16 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
         if (p.has_fir) {
             const int fir_r0 = first ? Hr : 0;
             for (int j0 = fir_r0 + warp * FB; j0 < rowsB; j0 += kNW * FB) {
-                T acc[FB];
+                // Each chunk of FB x-rows is summed in T, then folded into a double accumulator:
+                // a 257-term fp32 running sum alone costs ~2e-6 of the channel peak.
+                double acc[FB];
 #pragma unroll
-                for (int i = 0; i < FB; i++) acc[i] = T(0);
+                for (int i = 0; i < FB; i++) acc[i] = 0.0;
                 // y[j0+jj] = sum_k taps[k] * x[row j0+jj+Hf-k];  walk x rows r = j0 + rr
                 for (int r0 = 0; r0 < Hf + FB; r0 += FB) {
+                    T part[FB];
+#pragma unroll
+                    for (int i = 0; i < FB; i++) part[i] = T(0);
                     // tap for (rr = r0+i, jj): k = jj + Hf - r0 - i ; padded index k + tp_off
                     const int wbase = Hf - r0 + p.tp_off - (FB - 1);  // index of d = 0, d = jj - i + FB-1
                     T tw[2 * FB - 1];
@@ -219,12 +225,14 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
                     for (int i = 0; i < FB; i++) {
                         const T x = bufA[(j0 + r0 + i) * kCg + lane];
 #pragma unroll
-                        for (int jj = 0; jj < FB; jj++) acc[jj] += tw[jj - i + FB - 1] * x;
+                        for (int jj = 0; jj < FB; jj++) part[jj] += tw[jj - i + FB - 1] * x;
                     }
+#pragma unroll
+                    for (int jj = 0; jj < FB; jj++) acc[jj] += (double)part[jj];
                 }
 #pragma unroll
                 for (int jj = 0; jj < FB; jj++)
-                    if (j0 + jj < rowsB) bufB[(j0 + jj) * kCg + lane] = acc[jj] * p.g_fir;
+                    if (j0 + jj < rowsB) bufB[(j0 + jj) * kCg + lane] = (T)(acc[jj] * (double)p.g_fir);
             }
             __syncthreads();
         }
@@ -239,9 +247,9 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
             const int cbq1 = ra + (int)(((int64_t)(warp + 1) * nR) / kNW);
             // pass 1: zero-state end state of this warp's sub-chunk, z = sum_n A^(end-1-n) B y[n]
             {
-                T z0 = T(0), z1 = T(0);
+                double z0 = 0.0, z1 = 0.0;
                 for (int n = cbq; n < cbq1; n++) {
-                    const T x = y[n * kCg + lane];
+                    const double x = (double)y[n * kCg + lane];
                     const int k = cbq1 - 1 - n;
                     z0 += wt_s[2 * k] * x;
                     z1 += wt_s[2 * k + 1] * x;
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
             __syncthreads();
             if (warp == 0) {
                 // tile aggregate (zero-state end state over the whole chain region)
-                T Z0 = T(0), Z1 = T(0);
+                double Z0 = 0.0, Z1 = 0.0;
                 for (int q = 0; q < kNW; q++) {
                     const int lq = (int)(((int64_t)(q + 1) * nR) / kNW) - (int)(((int64_t)q * nR) / kNW);
                     mat2_apply(p.bq_apow + 4 * lq, Z0, Z1);
@@ -268,10 +276,10 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
                     if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
                 }
                 // incoming state
-                T S0, S1;
+                double S0, S1;
                 if (first) {
-                    S0 = cvalid ? p.bq_state[2 * c] : T(0);
-                    S1 = cvalid ? p.bq_state[2 * c + 1] : T(0);
+                    S0 = cvalid ? p.bq_state[2 * c] : 0.0;
+                    S1 = cvalid ? p.bq_state[2 * c + 1] : 0.0;
                 } else {
                     // decoupled look-back: lane i watches tile t-1-i
                     const int base = t - 1;
@@ -302,18 +310,18 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
                     const size_t s_inc = (size_t)g * p.n_tiles + (first_inc < 0 ? 0 : base - first_inc);
                     S0 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2);
                     S1 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2 + 1);
-                    const T *ML = p.bq_apow + 4 * L;  // every chained predecessor covers exactly L frames
+                    const double *ML = p.bq_apow + 4 * L;  // every chained predecessor covers exactly L frames
                     for (int i = first_inc - 1; i >= 0; i--) {
                         const size_t sa = (size_t)g * p.n_tiles + (base - i);
-                        const T a0 = ld_cg(p.lb_agg + sa * 64 + lane * 2);
-                        const T a1 = ld_cg(p.lb_agg + sa * 64 + lane * 2 + 1);
+                        const double a0 = ld_cg(p.lb_agg + sa * 64 + lane * 2);
+                        const double a1 = ld_cg(p.lb_agg + sa * 64 + lane * 2 + 1);
                         mat2_apply(ML, S0, S1);
                         S0 += a0;
                         S1 += a1;
                     }
                 }
                 // inclusive state after the chain region
-                T I0 = S0, I1 = S1;
+                double I0 = S0, I1 = S1;
                 mat2_apply(p.bq_apow + 4 * nR, I0, I1);
                 I0 += Z0;
                 I1 += Z1;
@@ -340,14 +348,15 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
             __syncthreads();
             // pass 2: the actual recurrence from the true incoming state, in place
             {
-                T s1 = sin_s[(warp * kCg + lane) * 2], s2 = sin_s[(warp * kCg + lane) * 2 + 1];
+                double s1 = sin_s[(warp * kCg + lane) * 2], s2 = sin_s[(warp * kCg + lane) * 2 + 1];
                 const int end = (warp == kNW - 1) ? rowsB : cbq1;
+                const double gbq = (double)p.g_bq;
                 for (int n = cbq; n < end; n++) {
-                    const T x = y[n * kCg + lane];
-                    const T v = p.b0 * x + s1;
+                    const double x = (double)y[n * kCg + lane];
+                    const double v = p.b0 * x + s1;
                     s1 = p.b1 * x - p.a1 * v + s2;
                     s2 = p.b2 * x - p.a2 * v;
-                    y[n * kCg + lane] = v * p.g_bq;
+                    y[n * kCg + lane] = (T)(v * gbq);
                 }
             }
             __syncthreads();
@@ -370,9 +379,14 @@ __global__ void __launch_bounds__(kTileThreads) chain_tile_kernel(const TilePara
                 const int br = (int)(up - 1 - (p.rs_acc0 + (im + 1) * up - (m + 1) * down));
                 const int row = (int)(im - f0) + Hr;
                 const T *__restrict__ cf = p.rs_coef + (size_t)br * P;
-                T acc = T(0);
-                for (int k = 0; k < P; k++) acc += __ldg(cf + k) * y[(row - k) * kCg + lane];
-                acc *= p.g_out;
+                double dacc = 0.0;
+                for (int k0 = 0; k0 < P; k0 += 8) {
+                    T part = T(0);
+                    const int k1 = (k0 + 8 < P) ? k0 + 8 : P;
+                    for (int k = k0; k < k1; k++) part += __ldg(cf + k) * y[(row - k) * kCg + lane];
+                    dacc += (double)part;
+                }
+                const T acc = (T)(dacc * (double)p.g_out);
                 if (cvalid) {
                     p.out[m * C + c] = acc;
                     if (meter) {
