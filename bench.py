@@ -55,13 +55,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(kernel_path: int):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
             with open(path) as f:
-                return json.load(f).get("dram_bytes_per_launch")
+                return json.load(f).get(str(kernel_path), {}).get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
@@ -297,7 +297,7 @@ def run_cuda(args):
                 "fused_meter_sink": bool(args.meter),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "traffic": ncu_traffic(path) if nb == BATCH_BUFFERS else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": samples_step * BYTES_PER_SAMPLE,
                          "kernel_ms": kern_ms},
             "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cpu_threads, "kind": "port",
