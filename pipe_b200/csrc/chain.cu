@@ -10,6 +10,7 @@
 #include <new>
 #include <vector>
 
+#include "chain_tc.cuh"
 #include "chain_tile.cuh"
 
 namespace pb {
@@ -40,6 +41,12 @@ struct Segment {
     // parameters (host, double)
     double g[4] = {1, 1, 1, 1};
     double b[3] = {1, 0, 0}, a[2] = {0, 0};
+    // K2 (tcgen05 path): eligibility, fp16 tables, fixed-point shifts, A^160
+    bool tc_ok = false;
+    void *d_tc_tables = nullptr;
+    int tc_sh = 0;
+    double tc_AL[4] = {1, 0, 0, 1};
+    double tc_W[2 * kTcFrames] = {0};
 };
 
 struct Slot {  // one in-flight batch of the pipelined host path
@@ -153,7 +160,7 @@ static void plan_segments(pb_chain *c)
 static void free_segment(Segment &s)
 {
     void *ptrs[] = {s.d_taps, s.d_wt, s.d_apow, s.d_coef, s.d_xhist[0], s.d_xhist[1], s.d_yhist[0], s.d_yhist[1],
-                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status};
+                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables};
     for (void *p : ptrs)
         if (p) cudaFree(p);
 }
@@ -172,6 +179,169 @@ static int32_t configure_kernel(pb_chain *c, Segment &s)
     PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, s.smem));
     if (per_sm < 1) return fail(PB_ERR_UNSUPPORTED, "fused tile kernel does not fit on an SM (%zu B shared)", s.smem);
     s.grid_max = per_sm * c->num_sms;
+    return PB_OK;
+}
+
+
+// ---- K2 host side --------------------------------------------------------------
+
+// fixed-point split: scale 2^shift so that |v| <= 2047 and sum|v| <= 8191 (with |x*2^10| <= 2048 every
+// partial sum of the exact accumulator then stays below 2^24)
+static int fixed_shift(const double *v, int n)
+{
+    double mx = 0, sum = 0;
+    for (int i = 0; i < n; i++) {
+        mx = std::max(mx, std::fabs(v[i]));
+        sum += std::fabs(v[i]);
+    }
+    if (mx == 0) return 0;
+    const double lim = std::min(2047.0 / mx, 8191.0 / sum);
+    int sh = (int)std::floor(std::log2(lim));
+    return std::max(-24, std::min(24, sh));
+}
+
+static void split_fixed3(double v, __half &p0, __half &p1, __half &p2)
+{
+    const double r = std::nearbyint(v);
+    p0 = __float2half_rn((float)r);
+    const double r1 = v - (double)__half2float(p0);
+    p1 = __float2half_rn((float)r1);
+    p2 = __float2half_rn((float)(r1 - (double)__half2float(p1)));
+}
+
+static int32_t build_tc_tables(pb_chain *c, Segment &s)
+{
+    const auto &fir = c->stages[s.fir_stage];
+    std::vector<double> h(kTcMaxTaps, 0.0);
+    for (size_t k = 0; k < fir.taps.size(); k++) h[k] = fir.taps[k];
+    auto gtap = [&](int t) { return (t >= 0 && t < kTcMaxTaps) ? h[(size_t)t] : 0.0; };
+    // biquad state response W[k] = A^k B and A^160
+    const double A[4] = {-s.a[0], 1.0, -s.a[1], 0.0};
+    const double B[2] = {s.b[1] - s.a[0] * s.b[0], s.b[2] - s.a[1] * s.b[0]};
+    double M[4] = {1, 0, 0, 1};
+    for (int k = 0; k <= kTcFrames; k++) {
+        if (k < kTcFrames) {
+            s.tc_W[2 * k] = M[0] * B[0] + M[1] * B[1];
+            s.tc_W[2 * k + 1] = M[2] * B[0] + M[3] * B[1];
+        } else {
+            for (int i = 0; i < 4; i++) s.tc_AL[i] = M[i];
+        }
+        const double N[4] = {M[0] * A[0] + M[1] * A[2], M[0] * A[1] + M[1] * A[3], M[2] * A[0] + M[3] * A[2],
+                             M[2] * A[1] + M[3] * A[3]};
+        for (int i = 0; i < 4; i++) M[i] = N[i];
+    }
+    s.tc_sh = fixed_shift(h.data(), kTcMaxTaps);
+    const double sh = std::ldexp(1.0, s.tc_sh);
+    std::vector<__half> tab((size_t)TcTables::kHalfs);
+    __half *T0 = tab.data(), *T1 = T0 + TcTables::kT, *T2 = T1 + TcTables::kT;
+    for (int e = -21; e <= 53; e++)
+        for (int n_i = 0; n_i < 8; n_i++)
+            for (int k_i = 0; k_i < 8; k_i++) {
+                const size_t idx = (size_t)(e + 21) * 64 + n_i * 8 + k_i;
+                split_fixed3(gtap(8 * e + n_i - k_i + 1) * sh, T0[idx], T1[idx], T2[idx]);
+            }
+    PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 2-D f32 tensor map over a [rows][C] frame-major buffer, box 32 channels x 16 frames, 128 B swizzle
+static int32_t make_frame_map(CUtensorMap *map, const void *base, int C, int64_t rows)
+{
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(PB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+    const cuuint32_t box[2] = {32, 16};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PB_OK;
+}
+
+static bool tc_shape_ok(const pb_chain *c, const Segment &s)
+{
+    if (c->dtype != PB_F32 || (c->flags & PB_CHAIN_NO_TENSOR) || c->C % kTcCh != 0) return false;
+    if (s.fir_stage < 0 || s.bq_stage < 0 || s.rs_stage < 0) return false;
+    if (s.Hf + 1 > kTcMaxTaps || s.Hf < 1) return false;
+    return s.up == kTcUp && s.down == kTcFrames && s.P == kTcP;
+}
+
+// One K2 launch: `n` (a multiple of 160) input frames of segment `s`.
+static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_t n, void *out, bool is_last_segment,
+                                 cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        attr_set = true;
+    }
+    TcParams p{};
+    int32_t r = make_frame_map(&p.tm_in, in, c->C, n);
+    if (r != PB_OK) return r;
+    r = make_frame_map(&p.tm_hist, s.d_xhist[s.pp], c->C, s.Hf);
+    if (r != PB_OK) return r;
+    p.out = (float *)out;
+    p.tables = (const __half *)s.d_tc_tables;
+    p.yhist = (const float *)s.d_yhist[s.pp];
+    p.yhist_next = (float *)s.d_yhist[s.pp ^ 1];
+    p.xhist_next = (float *)s.d_xhist[s.pp ^ 1];
+    p.bq_state = (const double *)s.d_state[s.pp];
+    p.bq_state_next = (double *)s.d_state[s.pp ^ 1];
+    p.lb_agg = (double *)s.d_agg;
+    p.lb_inc = (double *)s.d_inc;
+    p.lb_status = s.d_status;
+    const bool meter = is_last_segment && (c->flags & PB_CHAIN_METER);
+    p.meter_peak = meter ? c->d_meter : nullptr;
+    p.meter_sumsq = meter ? c->d_meter + c->C : nullptr;
+    p.err_flag = reinterpret_cast<int *>(c->d_ticket + 1);
+    p.C = c->C;
+    p.n_tiles = (int)(n / kTcFrames);
+    p.n_cg = c->C / kTcCh;
+    p.hist_rows = s.Hf;
+    c->epoch = (c->epoch % 0x3ffffffeu) + 1u;
+    p.epoch = c->epoch;
+    const double sx = 2048.0;
+    p.scale_in = (float)(s.g[0] * sx);
+    p.scale_hist = (float)sx;
+    p.inv_scale_in = (float)(1.0 / sx);
+    p.descale_fir = (float)(s.g[1] / (sx * std::ldexp(1.0, s.tc_sh)));
+    p.g_out = (float)s.g[3];
+    p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
+    p.g_bq = s.g[2];
+    for (int i = 0; i < 4; i++) p.AL[i] = s.tc_AL[i];
+    for (int k = 0; k < kTcFrames; k++) {
+        p.W[k][0] = s.tc_W[2 * k];
+        p.W[k][1] = s.tc_W[2 * k + 1];
+    }
+    const auto &rs = c->stages[s.rs_stage];
+    for (int br = 0; br < kTcUp; br++)
+        for (int k = 0; k < kTcP; k++) p.rs_coef[br * kTcP + k] = (float)rs.taps[(size_t)br + (size_t)k * kTcUp];
+    if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
+    const int total = p.n_tiles * p.n_cg;
+    const int grid = std::min(total, c->num_sms);
+    chain_tc_kernel<<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+    PB_CUDA(cudaGetLastError());
+    c->launches++;
+    s.pp ^= 1;
     return PB_OK;
 }
 
@@ -215,6 +385,7 @@ static int32_t refresh_segment_params(pb_chain *c, Segment &s)
             for (int k = 0; k < s.P; k++) coef[(size_t)br * s.P + k] = st.taps[(size_t)br + (size_t)k * s.up];
         PB_CUDA(upload_any(c->dtype, s.d_coef, coef));
     }
+    if (s.tc_ok) return build_tc_tables(c, s);
     return PB_OK;
 }
 
@@ -267,7 +438,7 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     if (s.bq_stage >= 0) {
         PB_CUDA(cudaMalloc(&s.d_apow, sizeof(double) * (size_t)s.apow_len * 4));
         PB_CUDA(cudaMalloc(&s.d_wt, sizeof(double) * (size_t)s.wt_len * 2));
-        s.lb_tiles = (int)ceil_div64(c->max_frames, s.L) + 1;
+        s.lb_tiles = (int)ceil_div64(c->max_frames, std::min(s.L, kTcFrames)) + 1;
         const size_t groups = (size_t)(c->C + kCg - 1) / kCg;
         PB_CUDA(cudaMalloc(&s.d_agg, sizeof(double) * groups * s.lb_tiles * 64));
         PB_CUDA(cudaMalloc(&s.d_inc, sizeof(double) * groups * s.lb_tiles * 64));
@@ -289,6 +460,8 @@ static int32_t build_segment(pb_chain *c, Segment &s)
             PB_CUDA(cudaMemset(s.d_state[i], 0, sizeof(double) * (size_t)c->C * 2));
         }
     }
+    s.tc_ok = tc_shape_ok(c, s);
+    if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_tables, sizeof(__half) * (size_t)TcTables::kHalfs));
     return refresh_segment_params(c, s);
 }
 
@@ -409,6 +582,7 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
     count_outputs(c, buf_frames, n_buffers, nullptr, &tin, &tout, false);
     if (tout > out_capacity_frames) return fail(PB_ERR_CAPACITY, "process: output needs %lld frames, capacity %lld", (long long)tout, (long long)out_capacity_frames);
     if (tin > 0 && (!in_dev || !out_dev)) return fail(PB_ERR_INVALID, "process: NULL buffer");
+    int path = 0;
     if (tin > 0) {
         const void *src = in_dev;
         int64_t n = tin;
@@ -416,9 +590,14 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
             Segment &s = c->segs[i];
             const bool lastseg = (i + 1 == c->segs.size());
             void *dst = lastseg ? out_dev : c->d_mid[i & 1];
-            int32_t r = c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, src, n, dst, lastseg, stream)
-                                           : launch_segment<double, 8>(c, s, src, n, dst, lastseg, stream);
+            // K2 needs the call aligned to 160-frame tiles (then the resampler phase is 0 at every tile start)
+            const bool use_tc = s.tc_ok && s.acc == 0 && n >= kTcFrames && n % kTcFrames == 0 &&
+                                ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
+            int32_t r = use_tc ? launch_segment_tc(c, s, src, n, dst, lastseg, stream)
+                        : c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, src, n, dst, lastseg, stream)
+                                             : launch_segment<double, 8>(c, s, src, n, dst, lastseg, stream);
             if (r != PB_OK) return r;
+            path = std::max(path, use_tc ? 2 : 1);
             if (s.rs_stage >= 0) n = (s.acc + n * s.up) / s.down;  // s.acc is committed below, after every launch used it
             src = dst;
             if (n == 0 && !lastseg) {
@@ -426,7 +605,7 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
                 break;
             }
         }
-        c->last_path = 1;
+        c->last_path = path;
     }
     count_outputs(c, buf_frames, n_buffers, buf_out_frames, &tin, &tout, true);
     c->meter_frames += tout;
@@ -616,7 +795,8 @@ extern "C" int32_t pb_chain_sync(pb_chain *c, void *stream)
     PB_CUDA(cudaStreamSynchronize(c->st_compute));
     int flag = 0;
     PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(PB_ERR_CUDA, "fused tile kernel: look-back wait timed out (kernel error flag set)");
+    if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fp16 fixed-point range (|g*x| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
+                                                    : "fused kernel: look-back wait timed out (kernel error flag set)");
     return PB_OK;
 }
 
@@ -713,7 +893,8 @@ extern "C" int32_t pb_chain_collect(pb_chain *c, int64_t *buf_out_frames, int32_
     {
         int flag = 0;
         PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
-        if (flag) return fail(PB_ERR_CUDA, "fused tile kernel: look-back wait timed out (kernel error flag set)");
+        if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fp16 fixed-point range (|g*x| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
+                                                        : "fused kernel: look-back wait timed out (kernel error flag set)");
     }
     if (sl.user_out && sl.out_frames) memcpy(sl.user_out, sl.h_out, c->elem * (size_t)sl.out_frames * c->C);
     if (buf_out_frames)
