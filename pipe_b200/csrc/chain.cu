@@ -6,6 +6,7 @@
 // and pb_chain_process* is the body of the resulting ProcessFunc
 // (pipe.go:64, invoked from Processor.execute at pipe.go:438).
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 #include <new>
 #include <vector>
@@ -47,6 +48,8 @@ struct Segment {
     int tc_sh = 0;
     double tc_AL[4] = {1, 0, 0, 1};
     double tc_W[2 * kTcFrames] = {0};
+    unsigned tc_emit[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<float> tc_seq;
 };
 
 struct Slot {  // one in-flight batch of the pipelined host path
@@ -241,6 +244,31 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 split_fixed3(gtap(8 * e + n_i - k_i + 1) * sh, T0[idx], T1[idx], T2[idx]);
             }
     PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    // Resampler coefficients per row in shift-register slot order (see the resampler warps in chain_tc.cuh).
+    // Output m is triggered by tile-relative frame i_m = ceil((m+1)*160/147) - 1 with branch 146 - ((i_m+1)*147 % 160);
+    // row R (frame i = R - 15) feeds tap k = i_m - i of every output with i_m in [i, i+15]; they are already ordered by m.
+    const auto &rs = c->stages[s.rs_stage];
+    std::vector<float> seq((size_t)TcTables::kSeq, 0.f);
+    for (int i = 0; i < 6; i++) s.tc_emit[i] = 0u;
+    for (int R = 0; R < kTcN - 1; R++) {
+        const int i = R - kTcHr;
+        const int m_lo = i <= 0 ? 0 : (i * kTcUp) / kTcFrames;   // outputs triggered before frame i are complete
+        int slot = 0;
+        for (int m = m_lo; m < kTcOut; m++) {
+            const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1;
+            if (im < i) continue;
+            if (im > i + 15) break;
+            const int k = im - i;
+            const int br = kTcUp - 1 - (((im + 1) * kTcUp) % kTcFrames);
+            if (slot >= 16) return fail(PB_ERR_UNSUPPORTED, "resampler schedule needs more than 16 in-flight outputs");
+            seq[(size_t)R * 16 + slot] = (float)rs.taps[(size_t)br + (size_t)k * kTcUp];
+            if (k == 0) s.tc_emit[R >> 5] |= 1u << (R & 31);  // the oldest in-flight output completes on this row
+            slot++;
+        }
+    }
+    PB_CUDA(cudaMemcpy((char *)s.d_tc_tables + (size_t)TcTables::kHalfs * 2, seq.data(), seq.size() * sizeof(float),
+                       cudaMemcpyHostToDevice));
+    s.tc_seq = seq;
     return PB_OK;
 }
 
@@ -329,17 +357,39 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     p.g_bq = s.g[2];
     for (int i = 0; i < 4; i++) p.AL[i] = s.tc_AL[i];
     for (int k = 0; k < kTcFrames; k++) {
-        p.W[k][0] = s.tc_W[2 * k];
-        p.W[k][1] = s.tc_W[2 * k + 1];
+        p.Wf[k][0] = (float)s.tc_W[2 * k];
+        p.Wf[k][1] = (float)s.tc_W[2 * k + 1];
     }
-    const auto &rs = c->stages[s.rs_stage];
-    for (int br = 0; br < kTcUp; br++)
-        for (int k = 0; k < kTcP; k++) p.rs_coef[br * kTcP + k] = (float)rs.taps[(size_t)br + (size_t)k * kTcUp];
+    for (int i = 0; i < 6; i++) p.rs_emit[i] = s.tc_emit[i];
     if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int total = p.n_tiles * p.n_cg;
     const int grid = std::min(total, c->num_sms);
+    // development aid: PB_TC_PROF=1 prints per-role cycle counters (averaged over CTAs) for every K2 launch
+    static const bool prof_on = getenv("PB_TC_PROF") != nullptr;
+    long long *d_prof = nullptr;
+    if (prof_on) {
+        PB_CUDA(cudaMalloc((void **)&d_prof, sizeof(long long) * tc::kProfCount * grid));
+        PB_CUDA(cudaMemset(d_prof, 0, sizeof(long long) * tc::kProfCount * grid));
+        p.prof = d_prof;
+    }
     chain_tc_kernel<<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
     PB_CUDA(cudaGetLastError());
+    if (prof_on) {
+        PB_CUDA(cudaStreamSynchronize(stream));
+        std::vector<long long> h((size_t)tc::kProfCount * grid);
+        PB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_prof);
+        static const char *names[] = {"prod_wait_empty", "mma_wait_tmem", "mma_wait_cvt", "mma_issue", "cvt_wait_raw",
+                                      "cvt_wait_cvt", "cvt_work", "bq_wait_tmem", "bq_drain", "bq_zpass", "bq_lookback",
+                                      "bq_main", "total", "rs_wait_y", "rs_main"};
+        const double tiles_per_cta = (double)total / grid;
+        fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
+        for (int k = 0; k <= tc::kProfRsMain; k++) {
+            double sum = 0;
+            for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + k];
+            fprintf(stderr, "  %-16s %10.0f\n", names[k], sum / grid / tiles_per_cta);
+        }
+    }
     c->launches++;
     s.pp ^= 1;
     return PB_OK;
@@ -461,7 +511,7 @@ static int32_t build_segment(pb_chain *c, Segment &s)
         }
     }
     s.tc_ok = tc_shape_ok(c, s);
-    if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_tables, sizeof(__half) * (size_t)TcTables::kHalfs));
+    if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_tables, (size_t)TcTables::kBytes));
     return refresh_segment_params(c, s);
 }
 

@@ -20,14 +20,19 @@
 // descriptor strides LBO = SBO = 128 B make 75 core matrices (9.6 KB per piece) serve all 27 x 22
 // positions.
 //
-// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 converters (f32 tile ->
-// x0/x1 in the MN-major UMMA layout), warps 6-9 epilogue (drain TMEM to a shared staging tile, then
-// per channel: double-precision biquad from the look-back state, statically unrolled polyphase
-// resampler, coalesced stores).  Tiles follow a static time-major schedule over a persistent grid.
+// Roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two converter groups
+// on alternate chunks (f32 tile -> x0/x1 in the MN-major UMMA layout), warps 10-13 biquad (drain half
+// of TMEM to a shared staging tile, look-back, double-precision recursion per channel, y written back in
+// place), warps 14-17 resampler (other half of the drain, then the statically unrolled 147/160 polyphase
+// streaming 16-row blocks behind the biquad warps, coalesced stores).  One warp per scheduler per role
+// exposed every latency (measured: 71 k cycles per tile, 50 k of them in a single-warp epilogue), hence
+// the split.  Tiles follow a static time-major schedule over a persistent grid.
 #pragma once
 
 #include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <utility>
 
 #include "chain_tile.cuh"
 
@@ -43,12 +48,16 @@ constexpr int kTcWin = kTcChunks * 16;
 constexpr int kTcLead = 272;        // frames of the window before the tile start
 constexpr int kTcMaxTaps = 257;
 constexpr int kTcCores = 75;        // Toeplitz core matrices per piece
-constexpr int kTcThreads = 320;
-constexpr int kRawStages = 4, kCvtStages = 4;
+constexpr int kTcThreads = 576;     // 18 warps: TMA, MMA, 2x4 converters, 4 biquad, 4 resampler
+constexpr int kRawStages = 8, kCvtStages = 4;
+constexpr int kTcSplit = 80;        // rows [0,80) drained / Z-summed by the biquad warps, [80,176) by the resampler warps
+constexpr int kTcBlocks = 11;       // 16-row hand-off blocks between the biquad and resampler warps
 
-struct TcTables {  // fp16 tables in global memory, copied to shared at kernel start: T0 T1 T2, 75*64 halfs each
-    static constexpr int kT = kTcCores * 64;
+struct TcTables {  // tables in global memory, copied to shared at kernel start
+    static constexpr int kT = kTcCores * 64;           // T0 T1 T2: 75*64 halfs each
     static constexpr int kHalfs = 3 * kT;
+    static constexpr int kSeq = kTcN * 16;              // then the resampler coefficients, [row][slot] floats (+1 spare row)
+    static constexpr int kBytes = kHalfs * 2 + kSeq * 4;
 };
 
 struct TcParams {
@@ -65,6 +74,7 @@ struct TcParams {
     unsigned *lb_status;
     double *meter_peak, *meter_sumsq;
     int *err_flag;
+    long long *prof;     // optional per-CTA cycle counters (PB_TC_PROF=1), nullptr otherwise
     int C, n_tiles, n_cg;
     int hist_rows;       // rows of xhist == FIR taps - 1 (<= 256)
     unsigned epoch;
@@ -75,8 +85,8 @@ struct TcParams {
     float g_out;
     double b0, b1, b2, a1, a2, g_bq;
     double AL[4];        // A^160
-    double W[kTcFrames][2];  // W[k] = A^k B: zero-state end state Z = sum_r W[159-r] * fir[r]
-    float rs_coef[kTcUp * kTcP];
+    float Wf[kTcFrames][2];  // W[k] = A^k B: zero-state end state Z = sum_r W[159-r] * fir[r]
+    unsigned rs_emit[6];  // bit r: row r completes an output (the oldest in-flight one)
 };
 
 #ifdef __CUDACC__
@@ -95,12 +105,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"  // suspend-time hint: park the warp in
+        "@p bra DONE;\n"                                               // hardware instead of spinning (a spinning
+        "bra WAIT_LOOP;\n"                                             // warp steals issue slots from its scheduler)
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -157,22 +167,54 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
         : "r"(taddr));
 }
 
+__device__ __forceinline__ long long clk() { return clock64(); }
+enum { kProfProdWait = 0, kProfMmaWaitTmem, kProfMmaWaitCvt, kProfMmaIssue, kProfCvtWaitRaw, kProfCvtWaitCvt, kProfCvtWork,
+       kProfEpiWaitTmem, kProfEpiDrain, kProfEpiZ, kProfEpiLookback, kProfEpiMain, kProfTotal, kProfRsWait, kProfRsMain, kProfCount = 16 };
+
 // shared memory map (bytes)
 constexpr int kRawStageBytes = 16 * kTcCh * 4;                  // 8 KB: 4 sub-tiles of 16 rows x 128 B
 constexpr int kCvtStageBytes = 2 * 16 * kTcCh * 2;              // 8 KB: x0 then x1
 constexpr int kOffRaw = 0;
 constexpr int kOffCvt = kOffRaw + kRawStages * kRawStageBytes;  // 32 KB
 constexpr int kOffTab = kOffCvt + kCvtStages * kCvtStageBytes;  // 64 KB
-constexpr int kTabBytes = TcTables::kHalfs * 2;                 // 28800
+constexpr int kTabBytes = TcTables::kBytes;                     // 28800 + 11200
 constexpr int kOffStage = ((kOffTab + kTabBytes + 127) / 128) * 128;
 constexpr int kStageBytes = kTcN * kTcCh * 4;                   // 90112: FIR output tile [176][128] f32
-constexpr int kOffBar = kOffStage + kStageBytes;
-constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + 2;
+constexpr int kOffZpart = kOffStage + kStageBytes;              // [4][32] double2: resampler warps' half of Z
+constexpr int kOffBar = kOffZpart + 4 * 32 * 16;
+constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + 2 + 4 + 4 * kTcBlocks + 4;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
 
 }  // namespace tc
+
+struct BqCoef {
+    double b0, b1, b2, na1, na2, gbq;
+};
+
+// ROWS rows of the TDF-II recursion for one channel, in place in the staging column.
+// All loads and conversions are issued up front; the loop-carried path is two DP operations per row:
+//   v = b0 x + s1;  s1' = (b1 x + s2) - a1 v;  s2' = b2 x - a2 v
+template <int ROWS>
+__device__ __forceinline__ void bq_block(float *__restrict__ col, const BqCoef &k, double &s1, double &s2)
+{
+    float xf[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) xf[i] = col[i * kTcCh];
+    double xd[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) xd[i] = (double)xf[i];
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) {
+        const double t = fma(k.b1, xd[i], s2);
+        const double p2 = k.b2 * xd[i];
+        const double v = fma(k.b0, xd[i], s1);
+        s1 = fma(k.na1, v, t);
+        s2 = fma(k.na2, v, p2);
+        col[i * kTcCh] = (float)(v * k.gbq);
+    }
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_constant__ TcParams p)
 {
@@ -181,11 +223,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     unsigned char *raw = smem + kOffRaw;
     unsigned char *cvt = smem + kOffCvt;
     __half *tab = reinterpret_cast<__half *>(smem + kOffTab);
+    const float *rs_seq = reinterpret_cast<const float *>(smem + kOffTab + TcTables::kHalfs * 2);
     float *stage = reinterpret_cast<float *>(smem + kOffStage);
+    double2 *zpart = reinterpret_cast<double2 *>(smem + kOffZpart);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
     uint64_t *raw_full = bars, *raw_empty = bars + kRawStages;
     uint64_t *cvt_full = bars + 2 * kRawStages, *cvt_empty = cvt_full + kCvtStages;
     uint64_t *tmem_full = cvt_empty + kCvtStages, *tmem_empty = tmem_full + 1;
+    uint64_t *zb_ready = tmem_empty + 1;            // [4]      resampler warp e -> biquad warp e: Z half is in zpart
+    uint64_t *yblk = zb_ready + 4;                  // [4][11]  biquad warp e -> resampler warp e: y block k is in the staging tile
+    uint64_t *wg2_done = yblk + 4 * kTcBlocks;      // [4]      resampler warp e finished the tile
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmemSlot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -206,7 +253,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&cvt_empty[i], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, 8);
+        for (int i = 0; i < 4; i++) {
+            mbar_init(&zb_ready[i], 1);
+            mbar_init(&wg2_done[i], 1);
+        }
+        for (int i = 0; i < 4 * kTcBlocks; i++) mbar_init(&yblk[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     {
@@ -219,18 +271,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: E [0,176), X [192,368)
-    constexpr uint32_t kColE = 0, kColX = 192;
+    constexpr uint32_t kColE = 0, kColX = 192;  // TMEM columns: E [0,176), X [192,368)
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int s = 0, ph = 0;
+            long long pw = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
                 const int f0 = t * kTcFrames, ch0 = cg * kTcCh;
                 for (int q = 0; q < kTcChunks; q++) {
+                    const long long c0 = clk();
                     mbar_wait(&raw_empty[s], ph ^ 1);
+                    pw += clk() - c0;
                     mbar_expect_tx(&raw_full[s], kRawStageBytes);
                     const int fr = f0 - kTcLead + 16 * q;  // first frame of the chunk, call-relative
                     // chunks never straddle frame 0 (kTcLead and tile starts are multiples of 16)
@@ -242,6 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     if (++s == kRawStages) { s = 0; ph ^= 1; }
                 }
             }
+            if (p.prof) p.prof[blockIdx.x * kProfCount + kProfProdWait] = pw;
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
@@ -249,11 +304,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const uint32_t t0 = smem_u32(tab), t1 = t0 + TcTables::kT * 2, t2 = t1 + TcTables::kT * 2;
             constexpr uint32_t idesc_main = make_idesc(kTcN);
             int s = 0, ph = 0, tph = 0;
+            long long w_t = 0, w_c = 0, w_i = 0;
+            const long long kstart = clk();
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(tmem_empty, tph ^ 1);  // epilogue has drained the previous tile
+                long long c0 = clk();
+                mbar_wait(tmem_empty, tph ^ 1);  // both halves of the previous tile have been drained
+                w_t += clk() - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int q = 0; q < kTcChunks; q++) {
+                    c0 = clk();
                     mbar_wait(&cvt_full[s], ph);
+                    const long long c1 = clk();
+                    w_c += c1 - c0;
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_base = smem_u32(cvt + s * kCvtStageBytes);
                     const uint64_t a0 = make_desc(a_base, 2048, 128), a1 = make_desc(a_base + 4096, 2048, 128);
@@ -267,117 +329,155 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     umma(tmem_base + kColX, a1, b0, idesc_main, 1);
                     umma(tmem_base + kColX, a1, b1, idesc_main, 1);
                     umma_commit(&cvt_empty[s]);  // frees the A stage when these MMAs have read it
+                    w_i += clk() - c1;
                     if (++s == kCvtStages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(tmem_full);
                 tph ^= 1;
             }
+            if (p.prof) {
+                long long *pr = p.prof + blockIdx.x * kProfCount;
+                pr[kProfMmaWaitTmem] = w_t;
+                pr[kProfMmaWaitCvt] = w_c;
+                pr[kProfMmaIssue] = w_i;
+                pr[kProfTotal] = clk() - kstart;
+            }
         }
-    } else if (warp < 6) {
+    } else if (warp < 10) {
         // ================================ converters ==================================
-        // warp cw handles channel sub-tile cw (32 channels); lane -> (fr_i = lane % 8, mbq = lane / 8)
-        const int cw = warp - 2;
+        // two groups of 4 warps take alternate chunks; in a group warp cw owns channel sub-tile cw
+        // (32 channels); lane -> (fr_i = lane % 8, mbq = lane / 8)
+        const int grp = (warp - 2) >> 2, cw = (warp - 2) & 3;
         const int fr_i = lane & 7, mbq = lane >> 3, mb = cw * 4 + mbq;
-        int rs = 0, rph = 0, cs = 0, cph = 0;
-        bool overflow = false;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        float vmax = 0.f;
+        long long w_r = 0, w_c = 0, w_w = 0;
+        const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int n_chunks = my_tiles * kTcChunks;
+        for (int g = grp; g < n_chunks; g += 2) {  // g: this CTA's running chunk number
+            const int it = g / kTcChunks, q = g - it * kTcChunks;
+            const int tile = blockIdx.x + it * gridDim.x;
             const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
             const int f0 = t * kTcFrames;
             const bool last = (t == p.n_tiles - 1);
-            for (int q = 0; q < kTcChunks; q++) {
-                mbar_wait(&raw_full[rs], rph);
-                mbar_wait(&cvt_empty[cs], cph ^ 1);
-                const bool hist = (f0 - kTcLead + 16 * q) < 0;
-                const float sc = hist ? p.scale_hist : p.scale_in;
-                const unsigned char *src = raw + rs * kRawStageBytes + cw * 2048;
-                unsigned char *dst = cvt + cs * kCvtStageBytes;
+            const int rs = g % kRawStages, rph = (g / kRawStages) & 1;
+            const int cs = g % kCvtStages, cph = (g / kCvtStages) & 1;
+            const long long c0 = clk();
+            mbar_wait(&raw_full[rs], rph);
+            const long long c1 = clk();
+            mbar_wait(&cvt_empty[cs], cph ^ 1);
+            const long long c2 = clk();
+            w_r += c1 - c0;
+            w_c += c2 - c1;
+            const bool hist = (f0 - kTcLead + 16 * q) < 0;
+            const float sc = hist ? p.scale_hist : p.scale_in;
+            const unsigned char *src = raw + rs * kRawStageBytes + cw * 2048;
+            unsigned char *dst = cvt + cs * kCvtStageBytes;
 #pragma unroll
-                for (int kb = 0; kb < 2; kb++) {
-                    const int row = 8 * kb + fr_i;
-                    // SWIZZLE_128B: 16 B chunk c of a row lives at chunk position c ^ (row % 8)
-                    const float4 va = *reinterpret_cast<const float4 *>(src + row * 128 + (((2 * mbq) ^ fr_i) << 4));
-                    const float4 vb = *reinterpret_cast<const float4 *>(src + row * 128 + (((2 * mbq + 1) ^ fr_i) << 4));
-                    float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-                    __half2 hi[4], lo[4];
+            for (int kb = 0; kb < 2; kb++) {
+                const int row = 8 * kb + fr_i;
+                // SWIZZLE_128B: 16 B chunk c of a row lives at chunk position c ^ (row % 8)
+                const float4 va = *reinterpret_cast<const float4 *>(src + row * 128 + (((2 * mbq) ^ fr_i) << 4));
+                const float4 vb = *reinterpret_cast<const float4 *>(src + row * 128 + (((2 * mbq + 1) ^ fr_i) << 4));
+                float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+                __half2 hi[4], lo[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float a = v[2 * i] * sc, b = v[2 * i + 1] * sc;
-                        const float ra = rintf(a), rb = rintf(b);
-                        hi[i] = __floats2half2_rn(ra, rb);
-                        lo[i] = __floats2half2_rn(a - ra, b - rb);
-                        overflow = overflow || fabsf(a) > 60000.f || fabsf(b) > 60000.f;
-                        v[2 * i] = a;
-                        v[2 * i + 1] = b;
-                    }
-                    const int off = (1 - kb) * 2048 + mb * 128 + fr_i * 16;  // K-blocks swapped (Toeplitz trick)
-                    *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<uint4 *>(hi);
-                    *reinterpret_cast<uint4 *>(dst + 4096 + off) = *reinterpret_cast<uint4 *>(lo);
-                    const int hrow = 16 * q + row - 176 - (256 - p.hist_rows);
-                    if (last && hrow >= 0) {
-                        // carried FIR input history: frames [n-hist_rows, n) in gain-scaled units (K1's convention)
-                        float *hp = p.xhist_next + (size_t)hrow * p.C + cg * kTcCh + mb * 8;
-                        const float is = p.inv_scale_in;
-                        *reinterpret_cast<float4 *>(hp) = make_float4(v[0] * is, v[1] * is, v[2] * is, v[3] * is);
-                        *reinterpret_cast<float4 *>(hp + 4) = make_float4(v[4] * is, v[5] * is, v[6] * is, v[7] * is);
-                    }
+                for (int i = 0; i < 4; i++) {
+                    const float a = v[2 * i] * sc, b = v[2 * i + 1] * sc;
+                    // round to nearest integer on the FMA pipe (exact for |a| < 2^22; larger values trip the range check)
+                    const float ra = (a + 12582912.f) - 12582912.f, rb = (b + 12582912.f) - 12582912.f;
+                    hi[i] = __floats2half2_rn(ra, rb);
+                    lo[i] = __floats2half2_rn(a - ra, b - rb);
+                    vmax = fmaxf(vmax, fmaxf(fabsf(a), fabsf(b)));
+                    v[2 * i] = a;
+                    v[2 * i + 1] = b;
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&cvt_full[cs]);
-                    mbar_arrive(&raw_empty[rs]);
+                const int off = (1 - kb) * 2048 + mb * 128 + fr_i * 16;  // K-blocks swapped (Toeplitz trick)
+                *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(dst + 4096 + off) = *reinterpret_cast<uint4 *>(lo);
+                const int hrow = 16 * q + row - 176 - (256 - p.hist_rows);
+                if (last && hrow >= 0) {
+                    // carried FIR input history: frames [n-hist_rows, n) in gain-scaled units (K1's convention)
+                    float *hp = p.xhist_next + (size_t)hrow * p.C + cg * kTcCh + mb * 8;
+                    const float is = p.inv_scale_in;
+                    *reinterpret_cast<float4 *>(hp) = make_float4(v[0] * is, v[1] * is, v[2] * is, v[3] * is);
+                    *reinterpret_cast<float4 *>(hp + 4) = make_float4(v[4] * is, v[5] * is, v[6] * is, v[7] * is);
                 }
-                if (++rs == kRawStages) { rs = 0; rph ^= 1; }
-                if (++cs == kCvtStages) { cs = 0; cph ^= 1; }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&cvt_full[cs]);
+                mbar_arrive(&raw_empty[rs]);
+            }
+            w_w += clk() - c2;
         }
-        if (overflow) atomicExch(p.err_flag, 2);
-    } else {
-        // ================================ epilogue ====================================
+        if (vmax > 60000.f) atomicExch(p.err_flag, 2);
+        if (p.prof && warp == 2 && lane == 0) {
+            long long *pr = p.prof + blockIdx.x * kProfCount;
+            pr[kProfCvtWaitRaw] = w_r;
+            pr[kProfCvtWaitCvt] = w_c;
+            pr[kProfCvtWork] = w_w;
+        }
+    } else if (warp < 14) {
+        // ================================ biquad warps ================================
         // warp e owns TMEM lanes [32e, 32e+32) == channels cg*128 + 32e + lane: an independent chain.
         const int e = warp & 3;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
         float *st = stage + e * 32 + lane;  // stage[row][128]: this thread's column
-        int tph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        long long e_w = 0, e_d = 0, e_z = 0, e_l = 0, e_m = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
             const bool first = (t == 0), last = (t == p.n_tiles - 1);
             const int c = cg * kTcCh + e * 32 + lane;
             const int grp = cg * 4 + e;  // 32-channel look-back group, same indexing as K1
-            mbar_wait(tmem_full, tph);
-            tph ^= 1;
+            const uint32_t par = it & 1;
+            const long long k0 = clk();
+            mbar_wait(tmem_full, par);
+            if (it > 0) mbar_wait(&wg2_done[e], par ^ 1);  // the resampler warp is done with the previous tile's rows
+            const long long k1 = clk();
+            e_w += k1 - k0;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            // ---- drain: FIR = (E + X) * descale into the staging tile; Z from the extra columns
-#pragma unroll 1
-            for (int c0 = 0; c0 < kTcN; c0 += 16) {
+            // ---- drain rows [0,80): FIR = (E + X) * descale into the staging tile; the look-back aggregate
+            //      Z = sum_r W[159-r] fir[r] is accumulated on the way (16-term float partial sums folded in double)
+            double Z0 = 0.0, Z1 = 0.0;
+            const bool chained = !first && !last;
+#pragma unroll
+            for (int c0 = 0; c0 < kTcSplit; c0 += 16) {
                 uint32_t re[16], rx[16];
                 tmem_ld16(tmem_base + lane_base + kColE + c0, re);
                 tmem_ld16(tmem_base + lane_base + kColX + c0, rx);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 16; i++) st[(c0 + i) * kTcCh] = (__uint_as_float(re[i]) + __uint_as_float(rx[i])) * p.descale_fir;
+                for (int i = 0; i < 16; i++) {
+                    const float v = (__uint_as_float(re[i]) + __uint_as_float(rx[i])) * p.descale_fir;
+                    st[(c0 + i) * kTcCh] = v;
+                    p0 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][0], v, p0);
+                    p1 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][1], v, p1);
+                }
+                Z0 += (double)p0;
+                Z1 += (double)p1;
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);  // the MMA warp may start the next tile
-
-            // ---- zero-state end state of the chain region (rows 0..159): the look-back aggregate
-            double Z0 = 0.0, Z1 = 0.0;
-            if (!first && !last) {
-#pragma unroll
-                for (int r = 0; r < kTcFrames; r++) {
-                    const double x = (double)st[r * kTcCh];
-                    Z0 += p.W[kTcFrames - 1 - r][0] * x;
-                    Z1 += p.W[kTcFrames - 1 - r][1] * x;
-                }
+            if (lane == 0) mbar_arrive(tmem_empty);
+            const long long k2 = clk();
+            e_d += k2 - k1;
+            mbar_wait(&zb_ready[e], par);  // also orders this warp after the other half of the drain
+            if (chained) {
+                const double2 zb = zpart[e * 32 + lane];
+                Z0 += zb.x;
+                Z1 += zb.y;
             }
+            const long long k3 = clk();
+            e_z += k3 - k2;
 
             // ---- biquad state chain (same protocol and arrays as K1, 32-channel groups)
             const size_t slot = (size_t)grp * p.n_tiles + t;
-            if (!first && !last) {
+            if (chained) {
                 p.lb_agg[slot * 64 + lane * 2] = Z0;
                 p.lb_agg[slot * 64 + lane * 2 + 1] = Z1;
-                __threadfence();
                 __syncwarp();
                 if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
             }
@@ -406,91 +506,193 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                         first_inc = -1;
                         break;
                     }
-                    __nanosleep(40);
+                    __nanosleep(20);
                 }
-                __threadfence();
                 __syncwarp();
                 const size_t s_inc = (size_t)grp * p.n_tiles + (first_inc < 0 ? 0 : base - first_inc);
                 s1 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2);
                 s2 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2 + 1);
-                for (int i = first_inc - 1; i >= 0; i--) {
-                    const size_t sa = (size_t)grp * p.n_tiles + (base - i);
-                    const double a0 = ld_cg(p.lb_agg + sa * 64 + lane * 2);
-                    const double a1 = ld_cg(p.lb_agg + sa * 64 + lane * 2 + 1);
-                    mat2_apply(p.AL, s1, s2);
-                    s1 += a0;
-                    s2 += a1;
+                // Horner over the aggregates between that inclusive state and this tile; payloads are fetched
+                // sixteen at a time so that only one L2 round trip per batch is exposed
+                for (int i0 = first_inc - 1; i0 >= 0; i0 -= 16) {
+                    double a0[16], a1[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const int i = i0 - u;
+                        const size_t sa = (size_t)grp * p.n_tiles + (base - (i >= 0 ? i : 0));
+                        a0[u] = ld_cg(p.lb_agg + sa * 64 + lane * 2);
+                        a1[u] = ld_cg(p.lb_agg + sa * 64 + lane * 2 + 1);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; u++)
+                        if (i0 - u >= 0) {
+                            mat2_apply(p.AL, s1, s2);
+                            s1 += a0[u];
+                            s2 += a1[u];
+                        }
                 }
             }
-            if (!first && !last) {
+            if (chained) {
                 double I0 = s1, I1 = s2;
                 mat2_apply(p.AL, I0, I1);
                 I0 += Z0;
                 I1 += Z1;
                 p.lb_inc[slot * 64 + lane * 2] = I0;
                 p.lb_inc[slot * 64 + lane * 2 + 1] = I1;
-                __threadfence();
                 __syncwarp();
                 if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
             }
+            const long long k4 = clk();
+            e_l += k4 - k3;
 
-            // ---- per channel: biquad recursion (double) + statically unrolled 147/160 polyphase
-            float w[16];
-            float *outp = p.out + (size_t)t * kTcOut * p.C + c;
-            double m_peak = 0.0, m_sumsq = 0.0;
-            const bool meter = p.meter_peak != nullptr;
-#pragma unroll
-            for (int r = 0; r < kTcN - 1; r++) {
-                float yv;
-                if (first && r < kTcHr) {
-                    yv = p.yhist[(size_t)r * p.C + c];  // tile 0: left context comes from the carried history
-                } else {
-                    const double x = (double)st[r * kTcCh];
-                    const double v = p.b0 * x + s1;
-                    s1 = p.b1 * x - p.a1 * v + s2;
-                    s2 = p.b2 * x - p.a2 * v;
-                    yv = (float)(v * p.g_bq);
-                }
-                w[r & 15] = yv;
-                if (r == kTcFrames - 1 && first && !last) {
-                    // tile 0 publishes its inclusive state (after frame 144) from the recursion itself
-                    p.lb_inc[slot * 64 + lane * 2] = s1;
-                    p.lb_inc[slot * 64 + lane * 2 + 1] = s2;
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
-                }
-                if (r >= kTcHr) {
-                    const int i = r - kTcHr;  // tile-relative input frame
-                    const int before = (i * kTcUp) / kTcFrames, after = ((i + 1) * kTcUp) / kTcFrames;
-                    if (after > before) {
-                        const int br = kTcUp - 1 - (((i + 1) * kTcUp) % kTcFrames);
-                        float a0 = 0.f, a1 = 0.f;  // two 8-term partial sums, folded in double (K1's summation shape)
-#pragma unroll
-                        for (int k = 0; k < 8; k++) a0 += p.rs_coef[br * kTcP + k] * w[(r - k) & 15];
-#pragma unroll
-                        for (int k = 8; k < 16; k++) a1 += p.rs_coef[br * kTcP + k] * w[(r - k) & 15];
-                        const float o = (float)(((double)a0 + (double)a1) * (double)p.g_out);
-                        outp[(size_t)before * p.C] = o;
-                        if (meter) {
-                            const double a = fabs((double)o);
-                            m_peak = a > m_peak ? a : m_peak;
-                            m_sumsq += (double)o * (double)o;
-                        }
-                    }
-                }
+            // ---- recursion in double, y written back over the FIR value; a block of 16 rows at a time is
+            //      handed to the resampler warp
+            const BqCoef kc = {p.b0, p.b1, p.b2, -p.a1, -p.a2, p.g_bq};
+            int k_start = 0;
+            if (first) {
+                // tile 0: the 15 left-context rows come from the carried history, the recursion starts at row 15
+                for (int r = 0; r < kTcHr; r++) st[r * kTcCh] = p.yhist[(size_t)r * p.C + c];
+                bq_block<1>(st + kTcHr * kTcCh, kc, s1, s2);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&yblk[e * kTcBlocks]);
+                k_start = 1;
             }
+#pragma unroll 1
+            for (int k = k_start; k < kTcBlocks - 1; k++) {
+                bq_block<16>(st + 16 * k * kTcCh, kc, s1, s2);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&yblk[e * kTcBlocks + k]);
+            }
+            if (first && !last) {
+                // tile 0 publishes its inclusive state (after row 159, frame 144) from the recursion itself
+                p.lb_inc[slot * 64 + lane * 2] = s1;
+                p.lb_inc[slot * 64 + lane * 2 + 1] = s2;
+                __syncwarp();
+                if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
+            }
+            bq_block<15>(st + 160 * kTcCh, kc, s1, s2);  // rows 160..174; column 175 is padding
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&yblk[e * kTcBlocks + kTcBlocks - 1]);
+            if (last)
+                for (int j = 0; j < kTcHr; j++) p.yhist_next[(size_t)j * p.C + c] = st[(kTcFrames + j) * kTcCh];
             if (last) {
                 p.bq_state_next[2 * c] = s1;
                 p.bq_state_next[2 * c + 1] = s2;
-#pragma unroll
-                for (int j = 0; j < kTcHr; j++) p.yhist_next[(size_t)j * p.C + c] = w[(kTcFrames + j) & 15];
             }
+            e_m += clk() - k4;
+        }
+        if (p.prof && warp == 10 && lane == 0) {
+            long long *pr = p.prof + blockIdx.x * kProfCount;
+            pr[kProfEpiWaitTmem] = e_w;
+            pr[kProfEpiDrain] = e_d;
+            pr[kProfEpiZ] = e_z;
+            pr[kProfEpiLookback] = e_l;
+            pr[kProfEpiMain] = e_m;
+        }
+    } else {
+        // ================================ resampler warps =============================
+        const int e = warp & 3;
+        const uint32_t lane_base = (uint32_t)(e * 32) << 16;
+        float *st = stage + e * 32 + lane;
+        long long r_w = 0, r_m = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
+            const bool first = (t == 0), last = (t == p.n_tiles - 1);
+            const int c = cg * kTcCh + e * 32 + lane;
+            const uint32_t par = it & 1;
+            mbar_wait(tmem_full, par);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            // ---- drain rows [80,176) with this warp's half of Z (rows [80,160)) accumulated on the way
+            double Z0 = 0.0, Z1 = 0.0;
+#pragma unroll
+            for (int c0 = kTcSplit; c0 < kTcN; c0 += 16) {
+                uint32_t re[16], rx[16];
+                tmem_ld16(tmem_base + lane_base + kColE + c0, re);
+                tmem_ld16(tmem_base + lane_base + kColX + c0, rx);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float v = (__uint_as_float(re[i]) + __uint_as_float(rx[i])) * p.descale_fir;
+                    st[(c0 + i) * kTcCh] = v;
+                    if (c0 + i < kTcFrames) {
+                        p0 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][0], v, p0);
+                        p1 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][1], v, p1);
+                    }
+                }
+                Z0 += (double)p0;
+                Z1 += (double)p1;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            zpart[e * 32 + lane] = make_double2(Z0, Z1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&zb_ready[e]);
+
+            // ---- 147/160 polyphase, input-driven, as a rolled loop over the y rows the biquad warp releases.
+            //      acc[0..15] are the in-flight outputs ordered by completion; every row adds its tap to each of
+            //      them, and on "emit" rows the oldest one is finished and the others move up one slot.  The host
+            //      lays the coefficients out per row in exactly that slot order (rs_seq), so the loop body is the
+            //      same 16 FFMAs for every row: compact code instead of 60 KB of unrolled, I-cache-missing SASS.
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[j] = 0.f;
+            float *outp = p.out + (size_t)t * kTcOut * p.C + c;
+            float m_peak = 0.f;
+            double m_sumsq = 0.0;
+            const bool meter = p.meter_peak != nullptr;
+            const float g_out = p.g_out;
+            const long long k5 = clk();
+#pragma unroll 1
+            for (int blk = 0; blk < kTcBlocks; blk++) {
+                const long long k6 = clk();
+                mbar_wait(&yblk[e * kTcBlocks + blk], par);
+                r_w += clk() - k6;
+                const int nrows = (blk == kTcBlocks - 1) ? 15 : 16;
+                const unsigned emask = (p.rs_emit[blk >> 1] >> ((blk & 1) * 16)) & ((1u << nrows) - 1u);
+                const float *col = st + 16 * blk * kTcCh;
+                const float4 *cq = reinterpret_cast<const float4 *>(rs_seq + 16 * blk * 16);
+                // Branch-free rows (a branch per row would pin every row's loads behind its reconvergence point):
+                // t[j] = cf[j]*y + acc[j]; on an emit row t[0] is the finished output and the others move up a slot.
+                // Rows past nrows have zero coefficients in the table and no emit bit, so they are no-ops.
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float y = col[(i < nrows ? i : nrows - 1) * kTcCh];
+                    const float4 c0 = cq[4 * i], c1 = cq[4 * i + 1], c2 = cq[4 * i + 2], c3 = cq[4 * i + 3];
+                    const float cf[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w,
+                                          c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+                    const bool emit = (emask >> i) & 1u;
+                    float tt[17];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) tt[j] = fmaf(cf[j], y, acc[j]);
+                    tt[16] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acc[j] = emit ? tt[j + 1] : tt[j];
+                    if (emit) {
+                        const float o = tt[0] * g_out;
+                        *outp = o;
+                        if (meter) {
+                            m_peak = fmaxf(m_peak, fabsf(o));
+                            m_sumsq += (double)o * (double)o;
+                        }
+                    }
+                    outp += emit ? p.C : 0;
+                }
+            }
+            r_m += clk() - k5;
             if (meter) {
-                atomic_max_nonneg(p.meter_peak + c, m_peak);
+                atomic_max_nonneg(p.meter_peak + c, (double)m_peak);
                 atomicAdd(p.meter_sumsq + c, m_sumsq);
             }
-            __syncwarp();  // the staging column is rewritten by the next drain
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&wg2_done[e]);
+        }
+        if (p.prof && warp == 14 && lane == 0) {
+            long long *pr = p.prof + blockIdx.x * kProfCount;
+            pr[kProfRsWait] = r_w;
+            pr[kProfRsMain] = r_m;
         }
     }
 

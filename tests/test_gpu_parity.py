@@ -333,3 +333,83 @@ def test_error_behaviour():
     with pytest.raises(abi.PipeB200Error) as e:
         gpu.set_stage(0, {"kind": "gain", "gain": 2.0})      # kind may not change
     assert e.value.code == abi.PB_ERR_INVALID
+
+
+# ------------------------------------------------------------ tcgen05 path (K2) --
+
+def _k2_chain(channels, bf, nb, flags=0):
+    return abi.Chain(channels, design.config_stages("chain4"), buffer_frames=bf, max_batch=nb, flags=flags)
+
+
+@pytest.mark.parametrize("channels,bf,nb", [(128, 160, 1), (128, 1600, 1), (256, 4096, 5), (1024, 1600, 2)])
+def test_k2_tensor_path_matches_oracle(channels, bf, nb):
+    # calls aligned to 160-frame tiles take the tcgen05/TMA kernel (path 2); same 1e-6 bar as K1
+    gpu, cpu = _k2_chain(channels, bf, nb), orc.Chain(channels, design.config_stages("chain4"))
+    for step in range(3):
+        x = signal_input(bf * nb, channels, seed=step)
+        refs = [cpu.process(x[i * bf:(i + 1) * bf], threads=os.cpu_count() or 1) for i in range(nb)]
+        y = gpu.process(x.astype(np.float32))
+        assert gpu.last_path()[0] == 2
+        assert len(y) == sum(len(r) for r in refs)
+        pos = 0
+        for i, r in enumerate(refs):
+            assert_parity(y[pos:pos + len(r)], r, REL_F32, f"step {step} buffer {i}")
+            pos += len(r)
+
+
+def test_k2_and_k1_share_carried_state():
+    # ragged calls fall back to K1 mid-stream; history, biquad state and resampler phase must carry across
+    ch = 128
+    gpu, cpu = _k2_chain(ch, 1600, 1), orc.Chain(ch, design.config_stages("chain4"))
+    paths = []
+    sizes = [1600, 1600, 100, 60, 1600, 37, 1440 + 123, 1600]   # 160-aligned again after 100+60 and 37+1563
+    x = signal_input(sum(sizes), ch, seed=5)
+    pos = 0
+    run_peak = np.zeros(ch)
+    for n in sizes:
+        blk = x[pos:pos + n]
+        pos += n
+        ref = cpu.process(blk)
+        run_peak = np.maximum(run_peak, np.abs(ref).max(axis=0))
+        y = gpu.process(blk.astype(np.float32))
+        paths.append(gpu.last_path()[0])
+        assert_parity(y, ref, REL_F32, f"{n} frames", floor=run_peak)
+    assert paths == [2, 2, 1, 1, 2, 1, 1, 2]
+
+
+def test_k2_no_tensor_flag_and_meter():
+    ch, bf = 128, 1600
+    x = signal_input(bf, ch, seed=9)
+    ref = orc.Chain(ch, design.config_stages("chain4")).process(x)
+    g1 = _k2_chain(ch, bf, 1, flags=abi.CHAIN_NO_TENSOR)
+    y1 = g1.process(x.astype(np.float32))
+    assert g1.last_path()[0] == 1
+    g2 = _k2_chain(ch, bf, 1, flags=abi.CHAIN_METER)
+    y2 = g2.process(x.astype(np.float32))
+    assert g2.last_path()[0] == 2
+    assert_parity(y1, ref, REL_F32)
+    assert_parity(y2, ref, REL_F32)
+    peak, sumsq, frames = g2.meter_read()
+    rp, rs = orc.meter(ref)
+    assert frames == len(ref)
+    np.testing.assert_allclose(peak, rp, rtol=2e-6)
+    np.testing.assert_allclose(sumsq, rs, rtol=2e-6)
+
+
+def test_k2_mutation_and_reset():
+    ch, bf = 128, 1600
+    st = design.config_stages("chain4")
+    gpu, cpu = abi.Chain(ch, st, buffer_frames=bf), orc.Chain(ch, st)
+    x = signal_input(3 * bf, ch, seed=11)
+    b2, a2 = design.biquad("lowpass", 3000.0, 48000.0, q=0.8)
+    for i in range(3):
+        if i == 1:
+            for c in (gpu, cpu):
+                c.set_stage(0, {"kind": "gain", "gain": 0.3})
+                c.set_stage(2, {"kind": "biquad", "b": b2, "a": a2})
+        blk = x[i * bf:(i + 1) * bf]
+        assert_parity(gpu.process(blk.astype(np.float32)), cpu.process(blk), REL_F32, f"buffer {i}")
+        assert gpu.last_path()[0] == 2
+    gpu.reset()
+    cpu.reset()
+    assert_parity(gpu.process(x[:bf].astype(np.float32)), cpu.process(x[:bf]), REL_F32, "after reset")
