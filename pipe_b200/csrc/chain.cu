@@ -366,6 +366,8 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     const int grid = std::min(total, c->num_sms);
     // development aid: PB_TC_PROF=1 prints per-role cycle counters (averaged over CTAs) for every K2 launch
     static const bool prof_on = getenv("PB_TC_PROF") != nullptr;
+    static const int dbg = getenv("PB_TC_DBG") ? atoi(getenv("PB_TC_DBG")) : 0;
+    p.dbg = dbg;
     long long *d_prof = nullptr;
     if (prof_on) {
         PB_CUDA(cudaMalloc((void **)&d_prof, sizeof(long long) * tc::kProfCount * grid));

@@ -75,6 +75,7 @@ struct TcParams {
     double *meter_peak, *meter_sumsq;
     int *err_flag;
     long long *prof;     // optional per-CTA cycle counters (PB_TC_PROF=1), nullptr otherwise
+    int dbg;             // development switches (PB_TC_DBG): bit0 skip the MMAs, bit1 skip the TMA loads
     int C, n_tiles, n_cg;
     int hist_rows;       // rows of xhist == FIR taps - 1 (<= 256)
     unsigned epoch;
@@ -323,11 +324,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     const uint64_t b0 = make_desc(t0 + toff, 128, 128), b1 = make_desc(t1 + toff, 128, 128);
                     const uint64_t b2 = make_desc(t2 + toff, 128, 128);
                     const uint32_t acc = q > 0;
-                    umma(tmem_base + kColE, a0, b0, idesc_main, acc);   // exact: integers < 2^24
-                    umma(tmem_base + kColX, a0, b1, idesc_main, acc);
-                    umma(tmem_base + kColX, a0, b2, idesc_main, 1);
-                    umma(tmem_base + kColX, a1, b0, idesc_main, 1);
-                    umma(tmem_base + kColX, a1, b1, idesc_main, 1);
+                    if (!(p.dbg & 1)) {
+                        umma(tmem_base + kColE, a0, b0, idesc_main, acc);   // exact: integers < 2^24
+                        umma(tmem_base + kColX, a0, b1, idesc_main, acc);
+                        umma(tmem_base + kColX, a0, b2, idesc_main, 1);
+                        umma(tmem_base + kColX, a1, b0, idesc_main, 1);
+                        umma(tmem_base + kColX, a1, b1, idesc_main, 1);
+                    }
                     umma_commit(&cvt_empty[s]);  // frees the A stage when these MMAs have read it
                     w_i += clk() - c1;
                     if (++s == kCvtStages) { s = 0; ph ^= 1; }
