@@ -48,8 +48,9 @@ struct Segment {
     int tc_sh = 0;
     double tc_AL[4] = {1, 0, 0, 1};
     double tc_W[2 * kTcFrames] = {0};
-    unsigned tc_emit[6] = {0, 0, 0, 0, 0, 0};
-    std::vector<float> tc_seq;
+    int tc_sh2 = 0;                                  // fixed-point shift of the resampler taps
+    double tc_AP48[4], tc_AP40[4], tc_AP24[4], tc_AP39[4];
+    std::vector<float> tc_rc;                        // [147][8] output correction per chain state (see chain_tc.cuh)
 };
 
 struct Slot {  // one in-flight batch of the pipelined host path
@@ -244,31 +245,95 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 split_fixed3(gtap(8 * e + n_i - k_i + 1) * sh, T0[idx], T1[idx], T2[idx]);
             }
     PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    // Resampler coefficients per row in shift-register slot order (see the resampler warps in chain_tc.cuh).
-    // Output m is triggered by tile-relative frame i_m = ceil((m+1)*160/147) - 1 with branch 146 - ((i_m+1)*147 % 160);
-    // row R (frame i = R - 15) feeds tap k = i_m - i of every output with i_m in [i, i+15]; they are already ordered by m.
+    // MMA2: the polyphase matrix of one tile, R[row][m] = coef[branch(m)][i_m - row], row = frame + 15.
+    // Output m is triggered by tile-relative frame i_m = ceil((m+1)*160/147) - 1 with branch 146 - ((i_m+1)*147 % 160).
+    // Slice s (outputs [32s, 32s+32)) reads row chunks [2s, 2s+4) (the last slice 3): 19 blocks [32 outputs][16 rows],
+    // K-major 8x8 core matrices, two fp16 pieces on the fixed grid 2^sh2.
     const auto &rs = c->stages[s.rs_stage];
-    std::vector<float> seq((size_t)TcTables::kSeq, 0.f);
-    for (int i = 0; i < 6; i++) s.tc_emit[i] = 0u;
-    for (int R = 0; R < kTcN - 1; R++) {
-        const int i = R - kTcHr;
-        const int m_lo = i <= 0 ? 0 : (i * kTcUp) / kTcFrames;   // outputs triggered before frame i are complete
-        int slot = 0;
-        for (int m = m_lo; m < kTcOut; m++) {
-            const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1;
-            if (im < i) continue;
-            if (im > i + 15) break;
-            const int k = im - i;
-            const int br = kTcUp - 1 - (((im + 1) * kTcUp) % kTcFrames);
-            if (slot >= 16) return fail(PB_ERR_UNSUPPORTED, "resampler schedule needs more than 16 in-flight outputs");
-            seq[(size_t)R * 16 + slot] = (float)rs.taps[(size_t)br + (size_t)k * kTcUp];
-            if (k == 0) s.tc_emit[R >> 5] |= 1u << (R & 31);  // the oldest in-flight output completes on this row
-            slot++;
+    auto rtap = [&](int row, int m) -> double {
+        if (m >= kTcOut) return 0.0;
+        const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1;
+        const int k = im + kTcHr - row;
+        if (k < 0 || k >= kTcP) return 0.0;
+        const int br = kTcUp - 1 - (((im + 1) * kTcUp) % kTcFrames);
+        return rs.taps[(size_t)br + (size_t)k * kTcUp];
+    };
+    {
+        std::vector<double> all;
+        for (int m = 0; m < kTcOut; m++) {
+            double sum = 0;  // the grid must keep sum|r0| of ONE output below 8191
+            for (int row = 0; row < kTcN; row++) sum += std::fabs(rtap(row, m));
+            all.push_back(sum);
+        }
+        double mx = 0, smax = 0;
+        for (size_t i = 0; i < rs.taps.size(); i++) mx = std::max(mx, std::fabs(rs.taps[i]));
+        for (double v : all) smax = std::max(smax, v);
+        int sh2 = 0;
+        if (mx > 0) sh2 = (int)std::floor(std::log2(std::min(2047.0 / mx, 8191.0 / smax)));
+        s.tc_sh2 = std::max(-24, std::min(24, sh2));
+    }
+    const double sh2 = std::ldexp(1.0, s.tc_sh2);
+    std::vector<__half> b2((size_t)TcTables::kB2);
+    int pair = 0;
+    for (int sl = 0; sl < kRsSlices; sl++) {
+        const int nch = (sl == kRsSlices - 1) ? 3 : 4;
+        for (int k = 0; k < nch; k++, pair++) {
+            const int chunk = 2 * sl + k;
+            for (int n = 0; n < kRsN; n++)
+                for (int kk = 0; kk < 16; kk++) {
+                    const double v = rtap(16 * chunk + kk, kRsN * sl + n) * sh2;
+                    const size_t idx = (size_t)(n / 8) * 128 + (size_t)(kk / 8) * 64 + (size_t)(n % 8) * 8 + (size_t)(kk % 8);
+                    __half r0 = __float2half_rn((float)std::nearbyint(v));
+                    __half r1 = __float2half_rn((float)(v - (double)__half2float(r0)));
+                    b2[(size_t)pair * 1024 + idx] = r0;
+                    b2[(size_t)pair * 1024 + 512 + idx] = r1;
+                }
         }
     }
-    PB_CUDA(cudaMemcpy((char *)s.d_tc_tables + (size_t)TcTables::kHalfs * 2, seq.data(), seq.size() * sizeof(float),
+    // every tap of every output must be inside the chunks its slice reads
+    for (int m = 0; m < kTcOut; m++) {
+        const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1, sl = m / kRsN;
+        const int lo = im, hi = im + kTcHr, nch = (sl == kRsSlices - 1) ? 3 : 4;
+        if (lo < 32 * sl || hi >= 32 * sl + 16 * nch) return fail(PB_ERR_UNSUPPORTED, "resampler slice schedule does not cover output %d", m);
+    }
+    PB_CUDA(cudaMemcpy((char *)s.d_tc_tables + (size_t)TcTables::kHalfs * 2, b2.data(), b2.size() * sizeof(__half),
                        cudaMemcpyHostToDevice));
-    s.tc_seq = seq;
+    // Biquad chains (rows 0-47, 48-95, 96-135, 136-175) run from a zero state; the response of output m to the true
+    // state q(j) at the start of chain j is rc[m][2j..2j+1] = g_bq g_out sum_{rows r of chain j} R[r][m] (A^(r-start_j))[0][.]
+    {
+        const int start[kBqChains + 1] = {8 * kBqHc0, 8 * kBqHc1, 8 * kBqHc2, 8 * kBqHc3, kTcN};
+        s.tc_rc.assign((size_t)kTcOut * 8, 0.f);
+        std::vector<double> acc((size_t)kTcOut * 8, 0.0);
+        for (int j = 0; j < kBqChains; j++) {
+            double Mk[4] = {1, 0, 0, 1};
+            for (int row = start[j]; row < start[j + 1]; row++) {
+                for (int m = 0; m < kTcOut; m++) {
+                    const double r = rtap(row, m);
+                    if (r != 0.0) {
+                        acc[(size_t)m * 8 + 2 * j] += r * Mk[0];
+                        acc[(size_t)m * 8 + 2 * j + 1] += r * Mk[1];
+                    }
+                }
+                const double N[4] = {Mk[0] * A[0] + Mk[1] * A[2], Mk[0] * A[1] + Mk[1] * A[3], Mk[2] * A[0] + Mk[3] * A[2],
+                                     Mk[2] * A[1] + Mk[3] * A[3]};
+                for (int i = 0; i < 4; i++) Mk[i] = N[i];
+            }
+        }
+        for (size_t i = 0; i < acc.size(); i++) s.tc_rc[i] = (float)(acc[i] * s.g[2] * s.g[3]);
+        auto mpow = [&](int n, double *out) {
+            double Mk[4] = {1, 0, 0, 1};
+            for (int k = 0; k < n; k++) {
+                const double N[4] = {Mk[0] * A[0] + Mk[1] * A[2], Mk[0] * A[1] + Mk[1] * A[3], Mk[2] * A[0] + Mk[3] * A[2],
+                                     Mk[2] * A[1] + Mk[3] * A[3]};
+                for (int i = 0; i < 4; i++) Mk[i] = N[i];
+            }
+            for (int i = 0; i < 4; i++) out[i] = Mk[i];
+        };
+        mpow(48, s.tc_AP48);
+        mpow(40, s.tc_AP40);
+        mpow(24, s.tc_AP24);
+        mpow(39, s.tc_AP39);
+    }
     return PB_OK;
 }
 
@@ -352,15 +417,23 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     p.scale_hist = (float)sx;
     p.inv_scale_in = (float)(1.0 / sx);
     p.descale_fir = (float)(s.g[1] / (sx * std::ldexp(1.0, s.tc_sh)));
-    p.g_out = (float)s.g[3];
+    p.descale_rs = (float)(s.g[3] / (sx * std::ldexp(1.0, s.tc_sh2)));
+    p.yh_scale = (float)sx;
     p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
     p.g_bq = s.g[2];
-    for (int i = 0; i < 4; i++) p.AL[i] = s.tc_AL[i];
+    p.ysc = s.g[2] * sx;
+    for (int i = 0; i < 4; i++) {
+        p.AL[i] = s.tc_AL[i];
+        p.AP48[i] = s.tc_AP48[i];
+        p.AP40[i] = s.tc_AP40[i];
+        p.AP24[i] = s.tc_AP24[i];
+        p.AP39[i] = s.tc_AP39[i];
+    }
+    memcpy(p.rc, s.tc_rc.data(), sizeof(p.rc));
     for (int k = 0; k < kTcFrames; k++) {
         p.Wf[k][0] = (float)s.tc_W[2 * k];
         p.Wf[k][1] = (float)s.tc_W[2 * k + 1];
     }
-    for (int i = 0; i < 6; i++) p.rs_emit[i] = s.tc_emit[i];
     if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int total = p.n_tiles * p.n_cg;
     const int grid = std::min(total, c->num_sms);
@@ -382,11 +455,11 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         PB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_prof);
         static const char *names[] = {"prod_wait_empty", "mma_wait_tmem", "mma_wait_cvt", "mma_issue", "cvt_wait_raw",
-                                      "cvt_wait_cvt", "cvt_work", "bq_wait_tmem", "bq_drain", "bq_zpass", "bq_lookback",
-                                      "bq_main", "total", "rs_wait_y", "rs_main"};
+                                      "cvt_wait_cvt", "cvt_work", "bq_wait_tmem", "bq_drain", "bq_zpass", "bq_main",
+                                      "bq_lookback", "total", "out_wait_d2", "out_main", "mma2_wait_y"};
         const double tiles_per_cta = (double)total / grid;
         fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
-        for (int k = 0; k <= tc::kProfRsMain; k++) {
+        for (int k = 0; k <= tc::kProfMma2Wait; k++) {
             double sum = 0;
             for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + k];
             fprintf(stderr, "  %-16s %10.0f\n", names[k], sum / grid / tiles_per_cta);

@@ -3,9 +3,14 @@
 // for that run when the call is aligned to 160-frame tiles; everything else goes through K1
 // (chain_tile.cuh), with which it shares every piece of carried state.
 //
-// FIR as a tensor-core contraction:  D[ch x frames] = X^T[ch x window] * Toeplitz[window x frames]
-//   M = 128 channels (TMEM lane = channel), N = 176 columns (15 left-context frames recomputed for
-//   the resampler + 160 frames + 1 pad), K = 432 input frames in 27 chunks of 16.
+// Two contractions per tile of 128 channels x 160 frames, both with channels on M (TMEM lane = channel):
+//
+//  MMA1 (FIR)        D1[ch x 176] = X^T[ch x 432] * Toeplitz[432 x 176]
+//      N = 176 columns (15 left-context frames recomputed for the resampler + 160 frames + 1 pad),
+//      K = 432 input frames in 27 chunks of 16.
+//  MMA2 (resampler)  D2[ch x 147] = Y^T[ch x 176] * R[176 x 147]
+//      R is the 147/160 polyphase matrix of the tile (every output has 16 taps, so R is a narrow band):
+//      five slices of 32 outputs, each touching 4 (the last: 3) chunks of 16 rows -- 19 (slice, chunk) blocks.
 //
 // Precision (measured with tools/tc_probe.cu): the tensor core adds into its fp32 accumulator with
 // truncation, which costs ~1e-6 over 27..81 steps.  So the operands are split on FIXED grids:
@@ -14,19 +19,34 @@
 //   grid, which summed over 257 taps was 5.7e-7 of the peak).  x0*h0 goes to accumulator E: every product
 //   and every partial sum is an integer below 2^24, so E is EXACT.  x0*h1 + x0*h2 + x1*h0 + x1*h1 go to
 //   accumulator X, 2^-9 of E in magnitude, whose truncation is negligible.  Modelled FIR error 6e-8.
+//   The resampler uses the same scheme with two pieces each (y*2^11 = y0 + y1, r*2^sh2 = r0 + r1; only 16
+//   taps per output): E2 = y0*r0 exact, X2 = y0*r1 + y1*r0 + y1*r1.  Modelled error 2.2e-7 of the peak, the
+//   same as the f32 FFMA chain it replaces.
 //
-// B operand: the Toeplitz matrix is never materialised.  A K-major 8x8 core matrix depends only on
+// B operand of MMA1: the Toeplitz matrix is never materialised.  A K-major 8x8 core matrix depends only on
 // (column block - row block); with the two K-blocks of an instruction stored swapped in A, the
 // descriptor strides LBO = SBO = 128 B make 75 core matrices (9.6 KB per piece) serve all 27 x 22
-// positions.
+// positions.  B operand of MMA2: the 19 blocks [32 outputs x 16 rows] of R, 1 KB per piece.
 //
-// Roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two converter groups
-// on alternate chunks (f32 tile -> x0/x1 in the MN-major UMMA layout), warps 10-13 biquad (drain half
-// of TMEM to a shared staging tile, look-back, double-precision recursion per channel, y written back in
-// place), warps 14-17 resampler (other half of the drain, then the statically unrolled 147/160 polyphase
-// streaming 16-row blocks behind the biquad warps, coalesced stores).  One warp per scheduler per role
-// exposed every latency (measured: 71 k cycles per tile, 50 k of them in a single-warp epilogue), hence
-// the split.  Tiles follow a static time-major schedule over a persistent grid.
+// Biquad between the two contractions: channel-per-lane, double precision.  The recursion is sequential in
+// time, so one thread runs FOUR zero-state chains (rows 0-47, 48-95, 96-135, 136-175) interleaved for
+// instruction-level parallelism and never waits for the state coming from the previous tile: y is linear in
+// that state, so its contribution is a rank-2 correction per chain, carried through the resampler on the host
+// (rc = R * (A^k)_row0) and added to the outputs when D2 is drained.  The state itself comes from the same
+// decoupled look-back as K1 (aggregate Z published right after the drain, inclusive state after the look-back),
+// which now overlaps MMA2 instead of stalling the recursion.
+//
+// Shared-memory staging: D1 is drained to an f32 tile so that TMEM is free for the next tile's MMA1 at once.
+// The biquad threads overwrite that tile IN PLACE with the fp16 pieces of y in the MN-major UMMA layout (one
+// 16-row chunk = 8 KB of f32 = 2 pieces x 4 KB of fp16; each warp's f32 values live inside the footprint of its
+// own 32 channels' pieces, a half-chunk of 8 rows is read completely before it is overwritten).  Core-matrix
+// stride 144 B instead of 128 B keeps the 2-byte scatter stores conflict-free.
+//
+// Roles (608 threads): warp 0 TMA producer, warp 1 MMA1 issuer, warps 2-5 / 6-9 two converter groups on
+// alternate chunks (f32 tile -> x0/x1 in the MN-major UMMA layout), warps 10-13 biquad (drain rows [0,80),
+// Z, recursion, pieces, look-back, chain states), warps 14-17 output (drain rows [80,176), then per slice:
+// D2 -> registers, correction, coalesced stores, meter), warp 18 MMA2 issuer.  Tiles follow a static
+// time-major schedule over a persistent grid.
 #pragma once
 
 #include <cuda.h>
@@ -48,16 +68,22 @@ constexpr int kTcWin = kTcChunks * 16;
 constexpr int kTcLead = 272;        // frames of the window before the tile start
 constexpr int kTcMaxTaps = 257;
 constexpr int kTcCores = 75;        // Toeplitz core matrices per piece
-constexpr int kTcThreads = 576;     // 18 warps: TMA, MMA, 2x4 converters, 4 biquad, 4 resampler
-constexpr int kRawStages = 8, kCvtStages = 4;
-constexpr int kTcSplit = 80;        // rows [0,80) drained / Z-summed by the biquad warps, [80,176) by the resampler warps
-constexpr int kTcBlocks = 11;       // 16-row hand-off blocks between the biquad and resampler warps
+constexpr int kTcThreads = 608;     // 19 warps: TMA, MMA1, 2x4 converters, 4 biquad, 4 output, MMA2
+constexpr int kRawStages = 4, kCvtStages = 3;
+constexpr int kTcSplit = 80;        // rows [0,80) drained / Z-summed by the biquad warps, [80,176) by the output warps
+constexpr int kTcRowChunks = kTcN / 16;  // 11 chunks of 16 rows of y (K of MMA2)
+constexpr int kRsSlices = 5;        // slices of 32 outputs; slice s reads row chunks [2s, 2s+4) (the last one 3)
+constexpr int kRsN = 32;
+constexpr int kRsPairs = 19;        // (slice, chunk) blocks of R
+constexpr int kBqChains = 4;        // zero-state recursion chains per tile, in half-chunks of 8 rows:
+constexpr int kBqHc0 = 0, kBqHc1 = 6, kBqHc2 = 12, kBqHc3 = 17;   //   first half-chunk of each chain
+constexpr int kBqLen0 = 6, kBqLen1 = 6, kBqLen2 = 5, kBqLen3 = 5; //   half-chunks per chain (rows 0,48,96,136)
 
 struct TcTables {  // tables in global memory, copied to shared at kernel start
     static constexpr int kT = kTcCores * 64;           // T0 T1 T2: 75*64 halfs each
     static constexpr int kHalfs = 3 * kT;
-    static constexpr int kSeq = kTcN * 16;              // then the resampler coefficients, [row][slot] floats (+1 spare row)
-    static constexpr int kBytes = kHalfs * 2 + kSeq * 4;
+    static constexpr int kB2 = kRsPairs * 2 * 512;      // then R blocks [pair][piece][nb 4][kb 2][8][8] halfs
+    static constexpr int kBytes = (kHalfs + kB2) * 2;
 };
 
 struct TcParams {
@@ -75,7 +101,7 @@ struct TcParams {
     double *meter_peak, *meter_sumsq;
     int *err_flag;
     long long *prof;     // optional per-CTA cycle counters (PB_TC_PROF=1), nullptr otherwise
-    int dbg;             // development switches (PB_TC_DBG): bit0 skip the MMAs, bit1 skip the TMA loads
+    int dbg;             // development switches (PB_TC_DBG): bit0 skip the MMAs
     int C, n_tiles, n_cg;
     int hist_rows;       // rows of xhist == FIR taps - 1 (<= 256)
     unsigned epoch;
@@ -83,11 +109,15 @@ struct TcParams {
     float scale_hist;    // 2^11          (history frames are already gain-scaled)
     float inv_scale_in;  // 2^-11: turns scaled input back into xhist_next values
     float descale_fir;   // g_fir / (2^11 * 2^sh)
-    float g_out;
-    double b0, b1, b2, a1, a2, g_bq;
-    double AL[4];        // A^160
-    float Wf[kTcFrames][2];  // W[k] = A^k B: zero-state end state Z = sum_r W[159-r] * fir[r]
-    unsigned rs_emit[6];  // bit r: row r completes an output (the oldest in-flight one)
+    float descale_rs;    // g_out / (2^11 * 2^sh2)
+    float yh_scale;      // 2^11: carried y history rows -> the fixed-point grid of the pieces
+    double b0, b1, b2, a1, a2;
+    double g_bq;         // gain after the biquad (y = v * g_bq)
+    double ysc;          // g_bq * 2^11
+    double AL[4];        // A^160 (look-back step)
+    double AP48[4], AP40[4], AP24[4], AP39[4];  // chain-to-chain / snapshot transitions
+    float Wf[kTcFrames][2];   // W[k] = A^k B: zero-state end state Z = sum_r W[159-r] * fir[r]
+    float rc[kTcOut][8];      // output correction: out[m] += sum_j rc[m][2j] * s(j)_1 + rc[m][2j+1] * s(j)_2
 };
 
 #ifdef __CUDACC__
@@ -168,54 +198,113 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
 __device__ __forceinline__ long long clk() { return clock64(); }
 enum { kProfProdWait = 0, kProfMmaWaitTmem, kProfMmaWaitCvt, kProfMmaIssue, kProfCvtWaitRaw, kProfCvtWaitCvt, kProfCvtWork,
-       kProfEpiWaitTmem, kProfEpiDrain, kProfEpiZ, kProfEpiLookback, kProfEpiMain, kProfTotal, kProfRsWait, kProfRsMain, kProfCount = 16 };
+       kProfBqWaitTmem, kProfBqDrain, kProfBqZ, kProfBqMain, kProfBqLookback, kProfTotal, kProfOutWait, kProfOutMain,
+       kProfMma2Wait, kProfCount = 16 };
 
 // shared memory map (bytes)
 constexpr int kRawStageBytes = 16 * kTcCh * 4;                  // 8 KB: 4 sub-tiles of 16 rows x 128 B
 constexpr int kCvtStageBytes = 2 * 16 * kTcCh * 2;              // 8 KB: x0 then x1
 constexpr int kOffRaw = 0;
-constexpr int kOffCvt = kOffRaw + kRawStages * kRawStageBytes;  // 32 KB
-constexpr int kOffTab = kOffCvt + kCvtStages * kCvtStageBytes;  // 64 KB
-constexpr int kTabBytes = TcTables::kBytes;                     // 28800 + 11200
+constexpr int kOffCvt = kOffRaw + kRawStages * kRawStageBytes;
+constexpr int kOffTab = kOffCvt + kCvtStages * kCvtStageBytes;
+constexpr int kTabBytes = TcTables::kBytes;                     // 28800 + 38912
+// staging tile: 11 chunks of 16 rows; a chunk is [piece 2][kb 2][mb 16] core matrices of 8 rows x 16 B at a
+// 144 B stride (see the header comment); the f32 FIR values of warp e live in the 576 B ranges of its own 4 mb
+constexpr int kMbStride = 144, kKbStride = 16 * kMbStride, kPieceBytes = 2 * kKbStride, kChunkBytes = 2 * kPieceBytes;
 constexpr int kOffStage = ((kOffTab + kTabBytes + 127) / 128) * 128;
-constexpr int kStageBytes = kTcN * kTcCh * 4;                   // 90112: FIR output tile [176][128] f32
-constexpr int kOffZpart = kOffStage + kStageBytes;              // [4][32] double2: resampler warps' half of Z
-constexpr int kOffBar = kOffZpart + 4 * 32 * 16;
-constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + 2 + 4 + 4 * kTcBlocks + 4;
+constexpr int kStageBytes = kTcRowChunks * kChunkBytes;         // 101376
+constexpr int kOffSstate = kOffStage + kStageBytes;             // [4][8][32] float chain states; aliases zpart [4][32] double2
+constexpr int kOffBar = kOffSstate + 4 * 8 * 32 * 4;
+constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + 2 + 4 + 1 + 1 + 2 + 2 + 4;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
+static_assert(kBqLen0 == kBqLen2 + 1 && kBqLen1 == kBqLen3 + 1 && kBqLen2 == kBqLen3, "chain schedule");
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
+static_assert(kOffStage % 16 == 0 && kChunkBytes % 16 == 0, "UMMA descriptor alignment");
+
+// TMEM columns: D1 = E [0,176) + X [192,368); D2 double-buffered slices E2/X2 of 32 columns from 368
+constexpr uint32_t kColE = 0, kColX = 192, kColD2 = 368;
+
+// byte offset of the f32 staging value of row r16 (0..15) of a chunk, relative to the thread's base
+__host__ __device__ constexpr int f32_off(int r16) { return (r16 >> 3) * kKbStride + ((r16 >> 2) & 1) * kPieceBytes + (r16 & 3) * 128; }
 
 }  // namespace tc
 
 struct BqCoef {
-    double b0, b1, b2, na1, na2, gbq;
+    double b0, b1, b2, na1, na2, ysc;
 };
 
-// ROWS rows of the TDF-II recursion for one channel, in place in the staging column.
-// All loads and conversions are issued up front; the loop-carried path is two DP operations per row:
-//   v = b0 x + s1;  s1' = (b1 x + s2) - a1 v;  s2' = b2 x - a2 v
-template <int ROWS>
-__device__ __forceinline__ void bq_block(float *__restrict__ col, const BqCoef &k, double &s1, double &s2)
+#ifdef __CUDACC__
+// One half-chunk (8 rows) of NCH independent TDF-II recursions for one channel, straight-line so that the chains
+// interleave:  v = b0 x + s1;  s1' = (b1 x + s2) - a1 v;  s2' = b2 x - a2 v;  y*2^11 = v * ysc is split into its fp16
+// pieces, which overwrite the f32 FIR values of the half-chunk in place (all lanes read them first).
+// g[j]: half-chunk of chain j.  HIST (tile 0 only, chain 0): rows < 15 are the carried y history, not recursion output.
+template <int NCH, bool HIST>
+__device__ __forceinline__ void bq_step(unsigned char *stf, unsigned char *stp, const int (&g)[NCH], const BqCoef &kc,
+                                        double *cs1, double *cs2, double &e3_1, double &e3_2, float &vmax,
+                                        const float *yh, int C, float yh_scale)
 {
-    float xf[ROWS];
+    using namespace tc;
+    float xf[NCH][8];
+    unsigned char *dst[NCH];
 #pragma unroll
-    for (int i = 0; i < ROWS; i++) xf[i] = col[i * kTcCh];
-    double xd[ROWS];
+    for (int j = 0; j < NCH; j++) {
+        const int off = (g[j] >> 1) * kChunkBytes + (g[j] & 1) * kKbStride;
+        const unsigned char *b = stf + off;
+        dst[j] = stp + off;
 #pragma unroll
-    for (int i = 0; i < ROWS; i++) xd[i] = (double)xf[i];
+        for (int rr = 0; rr < 8; rr++) xf[j][rr] = *reinterpret_cast<const float *>(b + (rr >> 2) * kPieceBytes + (rr & 3) * 128);
+    }
+    __syncwarp();  // every lane has read the half-chunks that the piece stores below overwrite
 #pragma unroll
-    for (int i = 0; i < ROWS; i++) {
-        const double t = fma(k.b1, xd[i], s2);
-        const double p2 = k.b2 * xd[i];
-        const double v = fma(k.b0, xd[i], s1);
-        s1 = fma(k.na1, v, t);
-        s2 = fma(k.na2, v, p2);
-        col[i * kTcCh] = (float)(v * k.gbq);
+    for (int rr = 0; rr < 8; rr++) {
+#pragma unroll
+        for (int j = 0; j < NCH; j++) {
+            const double x = (double)xf[j][rr];
+            const double tt = fma(kc.b1, x, cs2[j]);
+            const double p2 = kc.b2 * x;
+            const double v = fma(kc.b0, x, cs1[j]);
+            double n1 = fma(kc.na1, v, tt);
+            double n2 = fma(kc.na2, v, p2);
+            float a = (float)(v * kc.ysc);
+            if (HIST && j == 0) {
+                const int row = 8 * g[0] + rr;
+                const bool use = row < kTcHr;
+                const float yv = use ? yh[(size_t)row * C] : 0.f;
+                a = use ? yv * yh_scale : a;
+                n1 = use ? cs1[0] : n1;
+                n2 = use ? cs2[0] : n2;
+            }
+            cs1[j] = n1;
+            cs2[j] = n2;
+            const float ra = (a + 12582912.f) - 12582912.f;  // nearest integer (|a| < 2^22)
+            const __half h0 = __float2half_rn(ra);            // above 2048 the fp16 grid is coarser than 1:
+            const __half h1 = __float2half_rn(a - __half2float(h0));  // the remainder is taken from what h0 really holds
+            vmax = fmaxf(vmax, fabsf(a));
+            *reinterpret_cast<__half *>(dst[j] + rr * 16) = h0;
+            *reinterpret_cast<__half *>(dst[j] + rr * 16 + kPieceBytes) = h1;
+        }
+        if (NCH == kBqChains && rr == 6) {  // chain 3 after row 8g+6: on its last half-chunk that is row 174
+            e3_1 = cs1[3];
+            e3_2 = cs2[3];
+        }
     }
 }
+#endif
 
 __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_constant__ TcParams p)
 {
@@ -224,16 +313,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     unsigned char *raw = smem + kOffRaw;
     unsigned char *cvt = smem + kOffCvt;
     __half *tab = reinterpret_cast<__half *>(smem + kOffTab);
-    const float *rs_seq = reinterpret_cast<const float *>(smem + kOffTab + TcTables::kHalfs * 2);
-    float *stage = reinterpret_cast<float *>(smem + kOffStage);
-    double2 *zpart = reinterpret_cast<double2 *>(smem + kOffZpart);
+    unsigned char *stage = smem + kOffStage;
+    float *sstate = reinterpret_cast<float *>(smem + kOffSstate);
+    double2 *zpart = reinterpret_cast<double2 *>(smem + kOffSstate);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
     uint64_t *raw_full = bars, *raw_empty = bars + kRawStages;
     uint64_t *cvt_full = bars + 2 * kRawStages, *cvt_empty = cvt_full + kCvtStages;
     uint64_t *tmem_full = cvt_empty + kCvtStages, *tmem_empty = tmem_full + 1;
-    uint64_t *zb_ready = tmem_empty + 1;            // [4]      resampler warp e -> biquad warp e: Z half is in zpart
-    uint64_t *yblk = zb_ready + 4;                  // [4][11]  biquad warp e -> resampler warp e: y block k is in the staging tile
-    uint64_t *wg2_done = yblk + 4 * kTcBlocks;      // [4]      resampler warp e finished the tile
+    uint64_t *zb_ready = tmem_empty + 1;            // [4]  output warp e -> biquad warp e: rows [80,176) staged, Z half in zpart
+    uint64_t *y_ready = zb_ready + 4;               //      biquad warps -> MMA2: the y pieces of the tile are in the staging tile
+    uint64_t *stage_free = y_ready + 1;             //      MMA2 (commit) -> drain: the staging tile has been consumed
+    uint64_t *d2_full = stage_free + 1;             // [2]  MMA2 (commit) -> output warps
+    uint64_t *d2_empty = d2_full + 2;               // [2]  output warps -> MMA2
+    uint64_t *state_ready = d2_empty + 2;           // [4]  biquad warp e -> output warp e: chain states in sstate
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmemSlot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -257,9 +349,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         mbar_init(tmem_empty, 8);
         for (int i = 0; i < 4; i++) {
             mbar_init(&zb_ready[i], 1);
-            mbar_init(&wg2_done[i], 1);
+            mbar_init(&state_ready[i], 1);
         }
-        for (int i = 0; i < 4 * kTcBlocks; i++) mbar_init(&yblk[i], 1);
+        mbar_init(y_ready, 4);
+        mbar_init(stage_free, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&d2_full[i], 1);
+            mbar_init(&d2_empty[i], 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     {
@@ -272,7 +369,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t kColE = 0, kColX = 192;  // TMEM columns: E [0,176), X [192,368)
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -300,7 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             if (p.prof) p.prof[blockIdx.x * kProfCount + kProfProdWait] = pw;
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
+        // ================================ MMA1 issuer =================================
         if (lane == 0) {
             const uint32_t t0 = smem_u32(tab), t1 = t0 + TcTables::kT * 2, t2 = t1 + TcTables::kT * 2;
             constexpr uint32_t idesc_main = make_idesc(kTcN);
@@ -426,7 +522,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         // warp e owns TMEM lanes [32e, 32e+32) == channels cg*128 + 32e + lane: an independent chain.
         const int e = warp & 3;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
-        float *st = stage + e * 32 + lane;  // stage[row][128]: this thread's column
+        unsigned char *stf = stage + e * 4 * kMbStride + lane * 4;                        // f32 view: + chunk + f32_off(r16)
+        unsigned char *stp = stage + (e * 4 + (lane >> 3)) * kMbStride + (lane & 7) * 2;  // piece view: + chunk + piece + kb + fr*16
+        const BqCoef kc = {p.b0, p.b1, p.b2, -p.a1, -p.a2, p.ysc};
+        float vmax = 0.f;
         long long e_w = 0, e_d = 0, e_z = 0, e_l = 0, e_m = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
@@ -437,7 +536,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const uint32_t par = it & 1;
             const long long k0 = clk();
             mbar_wait(tmem_full, par);
-            if (it > 0) mbar_wait(&wg2_done[e], par ^ 1);  // the resampler warp is done with the previous tile's rows
+            if (it > 0) mbar_wait(stage_free, par ^ 1);  // MMA2 has consumed the previous tile's pieces
             const long long k1 = clk();
             e_w += k1 - k0;
             asm volatile("tcgen05.fence::after_thread_sync;");
@@ -455,7 +554,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const float v = (__uint_as_float(re[i]) + __uint_as_float(rx[i])) * p.descale_fir;
-                    st[(c0 + i) * kTcCh] = v;
+                    *reinterpret_cast<float *>(stf + (c0 >> 4) * kChunkBytes + f32_off(i)) = v;
                     p0 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][0], v, p0);
                     p1 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][1], v, p1);
                 }
@@ -468,27 +567,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const long long k2 = clk();
             e_d += k2 - k1;
             mbar_wait(&zb_ready[e], par);  // also orders this warp after the other half of the drain
+            const size_t slot = (size_t)grp * p.n_tiles + t;
             if (chained) {
                 const double2 zb = zpart[e * 32 + lane];
                 Z0 += zb.x;
                 Z1 += zb.y;
-            }
-            const long long k3 = clk();
-            e_z += k3 - k2;
-
-            // ---- biquad state chain (same protocol and arrays as K1, 32-channel groups)
-            const size_t slot = (size_t)grp * p.n_tiles + t;
-            if (chained) {
                 p.lb_agg[slot * 64 + lane * 2] = Z0;
                 p.lb_agg[slot * 64 + lane * 2 + 1] = Z1;
                 __syncwarp();
                 if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
             }
-            double s1, s2;
+            const long long k3 = clk();
+            e_z += k3 - k2;
+
+            // ---- four interleaved recursions in double over half-chunks of 8 rows; y*2^11 is split into
+            //      its fp16 pieces over the FIR values it was computed from
+            double cs1[kBqChains] = {0.0, 0.0, 0.0, 0.0}, cs2[kBqChains] = {0.0, 0.0, 0.0, 0.0};
+            double s159_1 = 0.0, s159_2 = 0.0, e3_1 = 0.0, e3_2 = 0.0;
+            const float *yh = p.yhist + c;
             if (first) {
-                s1 = p.bq_state[2 * c];
-                s2 = p.bq_state[2 * c + 1];
-            } else {
+                cs1[0] = p.bq_state[2 * c];
+                cs2[0] = p.bq_state[2 * c + 1];
+            }
+            {   // chains 0 and 1 are one half-chunk longer than chains 2 and 3: they take it first
+                const int g2[2] = {kBqHc0, kBqHc1};
+                if (first) bq_step<2, true>(stf, stp, g2, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
+                else bq_step<2, false>(stf, stp, g2, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
+            }
+#pragma unroll 1
+            for (int i = 0; i < kBqLen2; i++) {
+                const int g4[kBqChains] = {kBqHc0 + 1 + i, kBqHc1 + 1 + i, kBqHc2 + i, kBqHc3 + i};
+                if (first && i == 0) bq_step<kBqChains, true>(stf, stp, g4, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
+                else bq_step<kBqChains, false>(stf, stp, g4, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
+                if (i == 2) {  // chain 3 after row 159: the state the next tile's row 0 starts from
+                    s159_1 = cs1[3];
+                    s159_2 = cs2[3];
+                }
+            }
+            if (last) {
+                // carried y history rows 160..174, zero-state part (the state response is added below), read back
+                // from the pieces just written: y * 2^11 = y0 + y1
+                for (int r = 0; r < kTcHr; r++) {
+                    const unsigned char *d = stp + 10 * kChunkBytes + (r >> 3) * kKbStride + (r & 7) * 16;
+                    const float v = __half2float(*reinterpret_cast<const __half *>(d)) + __half2float(*reinterpret_cast<const __half *>(d + kPieceBytes));
+                    p.yhist_next[(size_t)r * p.C + c] = v / p.yh_scale;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(y_ready);
+            const long long k4 = clk();
+            e_m += k4 - k3;
+
+            // ---- incoming state: decoupled look-back (same protocol and arrays as K1, 32-channel groups)
+            double s1 = 0.0, s2 = 0.0;
+            if (!first) {
                 const int base = t - 1, j = base - lane;
                 int first_inc = 0;
                 for (unsigned spins = 0;; spins++) {
@@ -535,76 +668,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                         }
                 }
             }
-            if (chained) {
-                double I0 = s1, I1 = s2;
-                mat2_apply(p.AL, I0, I1);
-                I0 += Z0;
-                I1 += Z1;
+            // ---- true state at the start of every chain (chain 0 of tile 0 carried it itself: its entry is zero)
+            double q1[kBqChains], q2[kBqChains];
+            q1[0] = s1;
+            q2[0] = s2;
+#pragma unroll
+            for (int j = 1; j < kBqChains; j++) {
+                double u1 = q1[j - 1], u2 = q2[j - 1];
+                mat2_apply(j == 3 ? p.AP40 : p.AP48, u1, u2);
+                q1[j] = u1 + cs1[j - 1];
+                q2[j] = u2 + cs2[j - 1];
+            }
+            if (!last) {
+                // inclusive state after row 159 (== before the next tile's row 0)
+                double I0 = q1[3], I1 = q2[3];
+                mat2_apply(p.AP24, I0, I1);
+                I0 += s159_1;
+                I1 += s159_2;
                 p.lb_inc[slot * 64 + lane * 2] = I0;
                 p.lb_inc[slot * 64 + lane * 2 + 1] = I1;
                 __syncwarp();
                 if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
             }
-            const long long k4 = clk();
-            e_l += k4 - k3;
-
-            // ---- recursion in double, y written back over the FIR value; a block of 16 rows at a time is
-            //      handed to the resampler warp
-            const BqCoef kc = {p.b0, p.b1, p.b2, -p.a1, -p.a2, p.g_bq};
-            int k_start = 0;
-            if (first) {
-                // tile 0: the 15 left-context rows come from the carried history, the recursion starts at row 15
-                for (int r = 0; r < kTcHr; r++) st[r * kTcCh] = p.yhist[(size_t)r * p.C + c];
-                bq_block<1>(st + kTcHr * kTcCh, kc, s1, s2);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&yblk[e * kTcBlocks]);
-                k_start = 1;
+#pragma unroll
+            for (int j = 0; j < kBqChains; j++) {
+                sstate[(e * 8 + 2 * j) * 32 + lane] = (float)q1[j];
+                sstate[(e * 8 + 2 * j + 1) * 32 + lane] = (float)q2[j];
             }
-#pragma unroll 1
-            for (int k = k_start; k < kTcBlocks - 1; k++) {
-                bq_block<16>(st + 16 * k * kTcCh, kc, s1, s2);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&yblk[e * kTcBlocks + k]);
-            }
-            if (first && !last) {
-                // tile 0 publishes its inclusive state (after row 159, frame 144) from the recursion itself
-                p.lb_inc[slot * 64 + lane * 2] = s1;
-                p.lb_inc[slot * 64 + lane * 2 + 1] = s2;
-                __syncwarp();
-                if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
-            }
-            bq_block<15>(st + 160 * kTcCh, kc, s1, s2);  // rows 160..174; column 175 is padding
             __syncwarp();
-            if (lane == 0) mbar_arrive(&yblk[e * kTcBlocks + kTcBlocks - 1]);
-            if (last)
-                for (int j = 0; j < kTcHr; j++) p.yhist_next[(size_t)j * p.C + c] = st[(kTcFrames + j) * kTcCh];
+            if (lane == 0) mbar_arrive(&state_ready[e]);
             if (last) {
-                p.bq_state_next[2 * c] = s1;
-                p.bq_state_next[2 * c + 1] = s2;
+                // carried state: after row 174; carried y history: rows 160..174 with the state response added
+                double E0 = q1[3], E1 = q2[3];
+                mat2_apply(p.AP39, E0, E1);
+                p.bq_state_next[2 * c] = E0 + e3_1;
+                p.bq_state_next[2 * c + 1] = E1 + e3_2;
+                double u1 = q1[3], u2 = q2[3];
+                mat2_apply(p.AP24, u1, u2);
+                const double A[4] = {-p.a1, 1.0, -p.a2, 0.0};
+                for (int r = 0; r < kTcHr; r++) {
+                    float *hp = p.yhist_next + (size_t)r * p.C + c;
+                    *hp = (float)((double)*hp + u1 * p.g_bq);
+                    mat2_apply(A, u1, u2);
+                }
             }
-            e_m += clk() - k4;
+            e_l += clk() - k4;
         }
+        if (vmax > 60000.f) atomicExch(p.err_flag, 2);
         if (p.prof && warp == 10 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
-            pr[kProfEpiWaitTmem] = e_w;
-            pr[kProfEpiDrain] = e_d;
-            pr[kProfEpiZ] = e_z;
-            pr[kProfEpiLookback] = e_l;
-            pr[kProfEpiMain] = e_m;
+            pr[kProfBqWaitTmem] = e_w;
+            pr[kProfBqDrain] = e_d;
+            pr[kProfBqZ] = e_z;
+            pr[kProfBqMain] = e_m;
+            pr[kProfBqLookback] = e_l;
         }
-    } else {
-        // ================================ resampler warps =============================
+    } else if (warp < 18) {
+        // ================================ output warps ================================
         const int e = warp & 3;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
-        float *st = stage + e * 32 + lane;
+        unsigned char *stf = stage + e * 4 * kMbStride + lane * 4;
         long long r_w = 0, r_m = 0;
         int it = 0;
+        unsigned nsl = 0;  // running slice number: D2 buffer nsl & 1, phase (nsl >> 1) & 1
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
-            const bool first = (t == 0), last = (t == p.n_tiles - 1);
             const int c = cg * kTcCh + e * 32 + lane;
             const uint32_t par = it & 1;
             mbar_wait(tmem_full, par);
+            if (it > 0) mbar_wait(stage_free, par ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             // ---- drain rows [80,176) with this warp's half of Z (rows [80,160)) accumulated on the way
             double Z0 = 0.0, Z1 = 0.0;
@@ -618,7 +750,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const float v = (__uint_as_float(re[i]) + __uint_as_float(rx[i])) * p.descale_fir;
-                    st[(c0 + i) * kTcCh] = v;
+                    *reinterpret_cast<float *>(stf + (c0 >> 4) * kChunkBytes + f32_off(i)) = v;
                     if (c0 + i < kTcFrames) {
                         p0 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][0], v, p0);
                         p1 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][1], v, p1);
@@ -634,54 +766,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&zb_ready[e]);
 
-            // ---- 147/160 polyphase, input-driven, as a rolled loop over the y rows the biquad warp releases.
-            //      acc[0..15] are the in-flight outputs ordered by completion; every row adds its tap to each of
-            //      them, and on "emit" rows the oldest one is finished and the others move up one slot.  The host
-            //      lays the coefficients out per row in exactly that slot order (rs_seq), so the loop body is the
-            //      same 16 FFMAs for every row: compact code instead of 60 KB of unrolled, I-cache-missing SASS.
-            float acc[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) acc[j] = 0.f;
+            // ---- per slice: D2 -> registers, add the state response of the chains, store
             float *outp = p.out + (size_t)t * kTcOut * p.C + c;
+            float sv[8];
             float m_peak = 0.f;
             double m_sumsq = 0.0;
             const bool meter = p.meter_peak != nullptr;
-            const float g_out = p.g_out;
             const long long k5 = clk();
 #pragma unroll 1
-            for (int blk = 0; blk < kTcBlocks; blk++) {
+            for (int s = 0; s < kRsSlices; s++, nsl++) {
+                const uint32_t b = nsl & 1u;
                 const long long k6 = clk();
-                mbar_wait(&yblk[e * kTcBlocks + blk], par);
+                mbar_wait(&d2_full[b], (nsl >> 1) & 1u);
                 r_w += clk() - k6;
-                const int nrows = (blk == kTcBlocks - 1) ? 15 : 16;
-                const unsigned emask = (p.rs_emit[blk >> 1] >> ((blk & 1) * 16)) & ((1u << nrows) - 1u);
-                const float *col = st + 16 * blk * kTcCh;
-                const float4 *cq = reinterpret_cast<const float4 *>(rs_seq + 16 * blk * 16);
-                // Branch-free rows (a branch per row would pin every row's loads behind its reconvergence point):
-                // t[j] = cf[j]*y + acc[j]; on an emit row t[0] is the finished output and the others move up a slot.
-                // Rows past nrows have zero coefficients in the table and no emit bit, so they are no-ops.
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                uint32_t re[32], rx[32];
+                tmem_ld32(tmem_base + lane_base + kColD2 + 64 * b, re);
+                tmem_ld32(tmem_base + lane_base + kColD2 + 64 * b + 32, rx);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d2_empty[b]);
+                if (s == 0) {
+                    mbar_wait(&state_ready[e], par);
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float y = col[(i < nrows ? i : nrows - 1) * kTcCh];
-                    const float4 c0 = cq[4 * i], c1 = cq[4 * i + 1], c2 = cq[4 * i + 2], c3 = cq[4 * i + 3];
-                    const float cf[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w,
-                                          c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
-                    const bool emit = (emask >> i) & 1u;
-                    float tt[17];
+                    for (int q = 0; q < 8; q++) sv[q] = sstate[(e * 8 + q) * 32 + lane];
+                }
 #pragma unroll
-                    for (int j = 0; j < 16; j++) tt[j] = fmaf(cf[j], y, acc[j]);
-                    tt[16] = 0.f;
+                for (int i = 0; i < kRsN; i++) {
+                    const int m = kRsN * s + i;
+                    if (m < kTcOut) {
+                        float corr = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) acc[j] = emit ? tt[j + 1] : tt[j];
-                    if (emit) {
-                        const float o = tt[0] * g_out;
-                        *outp = o;
+                        for (int q = 0; q < 8; q++) corr = fmaf(p.rc[m][q], sv[q], corr);
+                        const float o = fmaf(__uint_as_float(re[i]) + __uint_as_float(rx[i]), p.descale_rs, corr);
+                        outp[(size_t)m * p.C] = o;
                         if (meter) {
                             m_peak = fmaxf(m_peak, fabsf(o));
                             m_sumsq += (double)o * (double)o;
                         }
                     }
-                    outp += emit ? p.C : 0;
                 }
             }
             r_m += clk() - k5;
@@ -689,13 +813,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 atomic_max_nonneg(p.meter_peak + c, (double)m_peak);
                 atomicAdd(p.meter_sumsq + c, m_sumsq);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&wg2_done[e]);
         }
         if (p.prof && warp == 14 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
-            pr[kProfRsWait] = r_w;
-            pr[kProfRsMain] = r_m;
+            pr[kProfOutWait] = r_w;
+            pr[kProfOutMain] = r_m;
+        }
+    } else {
+        // ================================ MMA2 issuer =================================
+        if (lane == 0) {
+            const uint32_t st0 = smem_u32(stage);
+            const uint32_t b2 = smem_u32(tab) + TcTables::kHalfs * 2;
+            constexpr uint32_t idesc_rs = make_idesc(kRsN);
+            unsigned nsl = 0;
+            int it = 0;
+            long long w_y = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+                const long long c0 = clk();
+                mbar_wait(y_ready, it & 1);
+                w_y += clk() - c0;
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                int pair = 0;
+                for (int s = 0; s < kRsSlices; s++, nsl++) {
+                    const uint32_t b = nsl & 1u;
+                    mbar_wait(&d2_empty[b], ((nsl >> 1) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t dE = tmem_base + kColD2 + 64 * b, dX = dE + 32;
+                    const int nch = (s == kRsSlices - 1) ? 3 : 4;
+                    for (int k = 0; k < nch; k++, pair++) {
+                        const uint32_t a_base = st0 + (2 * s + k) * kChunkBytes;
+                        const uint64_t a0 = make_desc(a_base, kKbStride, kMbStride), a1 = make_desc(a_base + kPieceBytes, kKbStride, kMbStride);
+                        const uint64_t r0 = make_desc(b2 + pair * 2048, 128, 256), r1 = make_desc(b2 + pair * 2048 + 1024, 128, 256);
+                        const uint32_t acc = k > 0;
+                        umma(dE, a0, r0, idesc_rs, acc);   // exact: integers < 2^24
+                        umma(dX, a0, r1, idesc_rs, acc);
+                        umma(dX, a1, r0, idesc_rs, 1);
+                        umma(dX, a1, r1, idesc_rs, 1);
+                    }
+                    umma_commit(&d2_full[b]);
+                }
+                umma_commit(stage_free);
+            }
+            if (p.prof) p.prof[blockIdx.x * kProfCount + kProfMma2Wait] = w_y;
         }
     }
 
