@@ -302,7 +302,6 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     // state q(j) at the start of chain j is rc[m][2j..2j+1] = g_bq g_out sum_{rows r of chain j} R[r][m] (A^(r-start_j))[0][.]
     {
         const int start[kBqChains + 1] = {8 * kBqHc0, 8 * kBqHc1, 8 * kBqHc2, 8 * kBqHc3, kTcN};
-        s.tc_rc.assign((size_t)kTcOut * 8, 0.f);
         std::vector<double> acc((size_t)kTcOut * 8, 0.0);
         for (int j = 0; j < kBqChains; j++) {
             double Mk[4] = {1, 0, 0, 1};
@@ -319,7 +318,16 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 for (int i = 0; i < 4; i++) Mk[i] = N[i];
             }
         }
-        for (size_t i = 0; i < acc.size(); i++) s.tc_rc[i] = (float)(acc[i] * s.g[2] * s.g[3]);
+        s.tc_rc.assign((size_t)kTcOut * 4, 0.f);
+        for (int m = 0; m < kTcOut; m++) {
+            const int j0 = rs_chain_of_slice(m / kRsN);
+            for (int j = 0; j < kBqChains; j++)
+                for (int q = 0; q < 2; q++) {
+                    const double v = acc[(size_t)m * 8 + 2 * j + q] * s.g[2] * s.g[3];
+                    if (j == j0 || j == j0 + 1) s.tc_rc[(size_t)m * 4 + 2 * (j - j0) + q] = (float)v;
+                    else if (v != 0.0) return fail(PB_ERR_UNSUPPORTED, "resampler output %d reads rows outside its two biquad chains", m);
+                }
+        }
         auto mpow = [&](int n, double *out) {
             double Mk[4] = {1, 0, 0, 1};
             for (int k = 0; k < n; k++) {
@@ -421,7 +429,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     p.yh_scale = (float)sx;
     p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
     p.g_bq = s.g[2];
-    p.ysc = s.g[2] * sx;
+    p.ysc = s.g[2] * sx * 8192.0;
     for (int i = 0; i < 4; i++) {
         p.AL[i] = s.tc_AL[i];
         p.AP48[i] = s.tc_AP48[i];
@@ -456,10 +464,11 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         cudaFree(d_prof);
         static const char *names[] = {"prod_wait_empty", "mma_wait_tmem", "mma_wait_cvt", "mma_issue", "cvt_wait_raw",
                                       "cvt_wait_cvt", "cvt_work", "bq_wait_tmem", "bq_drain", "bq_zpass", "bq_main",
-                                      "bq_lookback", "total", "out_wait_d2", "out_main", "mma2_wait_y"};
+                                      "bq_lookback", "total", "out_wait_d2", "out_main", "mma2_wait_y", "bqB_wait_tmem",
+                                      "bqB_drain", "bqB_wait_z", "bqB_main", "bqB_state"};
         const double tiles_per_cta = (double)total / grid;
         fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
-        for (int k = 0; k <= tc::kProfMma2Wait; k++) {
+        for (int k = 0; k <= tc::kProfBLookback; k++) {
             double sum = 0;
             for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + k];
             fprintf(stderr, "  %-16s %10.0f\n", names[k], sum / grid / tiles_per_cta);

@@ -68,13 +68,14 @@ constexpr int kTcWin = kTcChunks * 16;
 constexpr int kTcLead = 272;        // frames of the window before the tile start
 constexpr int kTcMaxTaps = 257;
 constexpr int kTcCores = 75;        // Toeplitz core matrices per piece
-constexpr int kTcThreads = 608;     // 19 warps: TMA, MMA1, 2x4 converters, 4 biquad, 4 output, MMA2
+constexpr int kTcThreads = 736;     // 23 warps: TMA, MMA1, 2x4 converters, 2x4 biquad, 4 output, MMA2
 constexpr int kRawStages = 4, kCvtStages = 3;
-constexpr int kTcSplit = 80;        // rows [0,80) drained / Z-summed by the biquad warps, [80,176) by the output warps
+constexpr int kTcDrainB = 64;       // rows [0,64) drained / Z-summed by biquad role A, [64,128) by role B, [128,176) by the output warps
 constexpr int kTcRowChunks = kTcN / 16;  // 11 chunks of 16 rows of y (K of MMA2)
 constexpr int kRsSlices = 5;        // slices of 32 outputs; slice s reads row chunks [2s, 2s+4) (the last one 3)
 constexpr int kRsN = 32;
 constexpr int kRsPairs = 19;        // (slice, chunk) blocks of R
+__host__ __device__ constexpr int rs_chain_of_slice(int s) { return s < 2 ? 0 : (s == 2 ? 1 : 2); }  // the two biquad chains (j, j+1) whose rows a slice reads
 constexpr int kBqChains = 4;        // zero-state recursion chains per tile, in half-chunks of 8 rows:
 constexpr int kBqHc0 = 0, kBqHc1 = 6, kBqHc2 = 12, kBqHc3 = 17;   //   first half-chunk of each chain
 constexpr int kBqLen0 = 6, kBqLen1 = 6, kBqLen2 = 5, kBqLen3 = 5; //   half-chunks per chain (rows 0,48,96,136)
@@ -101,7 +102,7 @@ struct TcParams {
     double *meter_peak, *meter_sumsq;
     int *err_flag;
     long long *prof;     // optional per-CTA cycle counters (PB_TC_PROF=1), nullptr otherwise
-    int dbg;             // development switches (PB_TC_DBG): bit0 skip the MMAs
+    int dbg;             // development switches (PB_TC_DBG): bit0 skip MMA1, bit1 skip MMA2, bit2 skip the conversion, bit4 skip the TMA loads
     int C, n_tiles, n_cg;
     int hist_rows;       // rows of xhist == FIR taps - 1 (<= 256)
     unsigned epoch;
@@ -113,11 +114,11 @@ struct TcParams {
     float yh_scale;      // 2^11: carried y history rows -> the fixed-point grid of the pieces
     double b0, b1, b2, a1, a2;
     double g_bq;         // gain after the biquad (y = v * g_bq)
-    double ysc;          // g_bq * 2^11
+    double ysc;          // g_bq * 2^11 * 2^13 (y -> fixed point with 13 fractional bits below the 2^11 grid)
     double AL[4];        // A^160 (look-back step)
     double AP48[4], AP40[4], AP24[4], AP39[4];  // chain-to-chain / snapshot transitions
     float Wf[kTcFrames][2];   // W[k] = A^k B: zero-state end state Z = sum_r W[159-r] * fir[r]
-    float rc[kTcOut][8];      // output correction: out[m] += sum_j rc[m][2j] * s(j)_1 + rc[m][2j+1] * s(j)_2
+    float rc[kTcOut][4];      // output correction: out[m] += rc[m][0..1] . q(j) + rc[m][2..3] . q(j+1), j = kRsChainOfSlice[m/32]
 };
 
 #ifdef __CUDACC__
@@ -213,7 +214,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 __device__ __forceinline__ long long clk() { return clock64(); }
 enum { kProfProdWait = 0, kProfMmaWaitTmem, kProfMmaWaitCvt, kProfMmaIssue, kProfCvtWaitRaw, kProfCvtWaitCvt, kProfCvtWork,
        kProfBqWaitTmem, kProfBqDrain, kProfBqZ, kProfBqMain, kProfBqLookback, kProfTotal, kProfOutWait, kProfOutMain,
-       kProfMma2Wait, kProfCount = 16 };
+       kProfMma2Wait, kProfBWaitTmem, kProfBDrain, kProfBZ, kProfBMain, kProfBLookback, kProfCount = 24 };
 
 // shared memory map (bytes)
 constexpr int kRawStageBytes = 16 * kTcCh * 4;                  // 8 KB: 4 sub-tiles of 16 rows x 128 B
@@ -229,7 +230,7 @@ constexpr int kOffStage = ((kOffTab + kTabBytes + 127) / 128) * 128;
 constexpr int kStageBytes = kTcRowChunks * kChunkBytes;         // 101376
 constexpr int kOffSstate = kOffStage + kStageBytes;             // [4][8][32] float chain states; aliases zpart [4][32] double2
 constexpr int kOffBar = kOffSstate + 4 * 8 * 32 * 4;
-constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + 2 + 4 + 1 + 1 + 2 + 2 + 4;
+constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + 2 + 4 + 1 + 1 + 2 + 2 + 4 + 4;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
 static_assert(kBqLen0 == kBqLen2 + 1 && kBqLen1 == kBqLen3 + 1 && kBqLen2 == kBqLen3, "chain schedule");
@@ -253,12 +254,13 @@ struct BqCoef {
 // interleave:  v = b0 x + s1;  s1' = (b1 x + s2) - a1 v;  s2' = b2 x - a2 v;  y*2^11 = v * ysc is split into its fp16
 // pieces, which overwrite the f32 FIR values of the half-chunk in place (all lanes read them first).
 // g[j]: half-chunk of chain j.  HIST (tile 0 only, chain 0): rows < 15 are the carried y history, not recursion output.
-template <int NCH, bool HIST>
+template <int NCH, bool HIST, bool CAP>
 __device__ __forceinline__ void bq_step(unsigned char *stf, unsigned char *stp, const int (&g)[NCH], const BqCoef &kc,
                                         double *cs1, double *cs2, double &e3_1, double &e3_2, float &vmax,
                                         const float *yh, int C, float yh_scale)
 {
     using namespace tc;
+    bool oflow = false;
     float xf[NCH][8];
     unsigned char *dst[NCH];
 #pragma unroll
@@ -274,35 +276,46 @@ __device__ __forceinline__ void bq_step(unsigned char *stf, unsigned char *stp, 
     for (int rr = 0; rr < 8; rr++) {
 #pragma unroll
         for (int j = 0; j < NCH; j++) {
-            const double x = (double)xf[j][rr];
+            // f32 -> f64 and f64 -> fixed point by bit manipulation: the F2F conversions that involve a 64-bit type
+            // cost ~40 cycles per warp on this part (measured: they, not the DFMAs, bounded the recursion)
+            const unsigned xu = __float_as_uint(xf[j][rr]);
+            const unsigned xa = xu & 0x7fffffffu;
+            const int xhi = (int)((xu & 0x80000000u) | (xa < 0x00800000u ? 0u : (xa >> 3) + 0x38000000u));  // zero / denormal -> 0
+            const double x = __hiloint2double(xhi, (int)(xu << 29));
             const double tt = fma(kc.b1, x, cs2[j]);
             const double p2 = kc.b2 * x;
             const double v = fma(kc.b0, x, cs1[j]);
             double n1 = fma(kc.na1, v, tt);
             double n2 = fma(kc.na2, v, p2);
-            float a = (float)(v * kc.ysc);
+            // K = rint(y * 2^11 * 2^13) from the low word of v * ysc13 + 1.5 * 2^52;  y * 2^11 = i + k / 2^13
+            const double rk = fma(v, kc.ysc, 6755399441055744.0);
+            int K = __double2loint(rk);
+            oflow |= (unsigned)(__double2hiint(rk) + 1 - 0x43380000) > 1u;  // |y * 2^24| >= 2^31: K has wrapped
             if (HIST && j == 0) {
                 const int row = 8 * g[0] + rr;
                 const bool use = row < kTcHr;
                 const float yv = use ? yh[(size_t)row * C] : 0.f;
-                a = use ? yv * yh_scale : a;
+                K = use ? __float2int_rn(yv * yh_scale * 8192.f) : K;
                 n1 = use ? cs1[0] : n1;
                 n2 = use ? cs2[0] : n2;
             }
             cs1[j] = n1;
             cs2[j] = n2;
-            const float ra = (a + 12582912.f) - 12582912.f;  // nearest integer (|a| < 2^22)
+            const int ii = (K + 4096) >> 13, kk = K - (ii << 13);
+            const float ra = __int_as_float(0x4B400000 + ii) - 12582912.f;   // exact int -> float for |.| < 2^22
+            const float fk = __int_as_float(0x4B400000 + kk) - 12582912.f;
             const __half h0 = __float2half_rn(ra);            // above 2048 the fp16 grid is coarser than 1:
-            const __half h1 = __float2half_rn(a - __half2float(h0));  // the remainder is taken from what h0 really holds
-            vmax = fmaxf(vmax, fabsf(a));
+            const __half h1 = __float2half_rn(fmaf(fk, 1.f / 8192.f, ra - __half2float(h0)));  // the remainder is taken from what h0 really holds
+            vmax = fmaxf(vmax, fabsf(ra));
             *reinterpret_cast<__half *>(dst[j] + rr * 16) = h0;
             *reinterpret_cast<__half *>(dst[j] + rr * 16 + kPieceBytes) = h1;
         }
-        if (NCH == kBqChains && rr == 6) {  // chain 3 after row 8g+6: on its last half-chunk that is row 174
-            e3_1 = cs1[3];
-            e3_2 = cs2[3];
+        if (CAP && rr == 6) {  // last chain of the call after row 8g+6: on chain 3's last half-chunk that is row 174
+            e3_1 = cs1[NCH - 1];
+            e3_2 = cs2[NCH - 1];
         }
     }
+    if (oflow) vmax = 1e30f;
 }
 #endif
 
@@ -320,12 +333,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     uint64_t *raw_full = bars, *raw_empty = bars + kRawStages;
     uint64_t *cvt_full = bars + 2 * kRawStages, *cvt_empty = cvt_full + kCvtStages;
     uint64_t *tmem_full = cvt_empty + kCvtStages, *tmem_empty = tmem_full + 1;
-    uint64_t *zb_ready = tmem_empty + 1;            // [4]  output warp e -> biquad warp e: rows [80,176) staged, Z half in zpart
+    uint64_t *zb_ready = tmem_empty + 1;            // [4]  biquad warp B and output warp e -> biquad warps e: rows staged, Z parts in zpart
     uint64_t *y_ready = zb_ready + 4;               //      biquad warps -> MMA2: the y pieces of the tile are in the staging tile
     uint64_t *stage_free = y_ready + 1;             //      MMA2 (commit) -> drain: the staging tile has been consumed
     uint64_t *d2_full = stage_free + 1;             // [2]  MMA2 (commit) -> output warps
     uint64_t *d2_empty = d2_full + 2;               // [2]  output warps -> MMA2
-    uint64_t *state_ready = d2_empty + 2;           // [4]  biquad warp e -> output warp e: chain states in sstate
+    uint64_t *state_ready = d2_empty + 2;           // [4]  biquad warps e (A and B) -> output warp e: chain states in sstate
+    uint64_t *q2_ready = state_ready + 4;           // [4]  biquad warp A -> B: state at the start of chain 2 in the q2 slot
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmemSlot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -346,12 +360,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&cvt_empty[i], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 8);
+        mbar_init(tmem_empty, 12);
         for (int i = 0; i < 4; i++) {
-            mbar_init(&zb_ready[i], 1);
-            mbar_init(&state_ready[i], 1);
+            mbar_init(&zb_ready[i], 2);
+            mbar_init(&state_ready[i], 2);
+            mbar_init(&q2_ready[i], 1);
         }
-        mbar_init(y_ready, 4);
+        mbar_init(y_ready, 8);
         mbar_init(stage_free, 1);
         for (int i = 0; i < 2; i++) {
             mbar_init(&d2_full[i], 1);
@@ -382,6 +397,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     const long long c0 = clk();
                     mbar_wait(&raw_empty[s], ph ^ 1);
                     pw += clk() - c0;
+                    if (p.dbg & 16) {  // development: no loads
+                        mbar_arrive(&raw_full[s]);
+                        if (++s == kRawStages) { s = 0; ph ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&raw_full[s], kRawStageBytes);
                     const int fr = f0 - kTcLead + 16 * q;  // first frame of the chunk, call-relative
                     // chunks never straddle frame 0 (kTcLead and tile starts are multiples of 16)
@@ -399,7 +419,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         // ================================ MMA1 issuer =================================
         if (lane == 0) {
             const uint32_t t0 = smem_u32(tab), t1 = t0 + TcTables::kT * 2, t2 = t1 + TcTables::kT * 2;
-            constexpr uint32_t idesc_main = make_idesc(kTcN);
             int s = 0, ph = 0, tph = 0;
             long long w_t = 0, w_c = 0, w_i = 0;
             const long long kstart = clk();
@@ -416,16 +435,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_base = smem_u32(cvt + s * kCvtStageBytes);
                     const uint64_t a0 = make_desc(a_base, 2048, 128), a1 = make_desc(a_base + 4096, 2048, 128);
-                    const uint32_t toff = (52 - 2 * q) * 128;
+                    // Only the band of the Toeplitz matrix is multiplied: chunk q (frames f0-272+16q ..+15) reaches output
+                    // columns [16q-257, 16q+14], i.e. 8-column blocks [2q-33, 2q+1] clipped to [0, 21] and widened to an even
+                    // count (N % 16 == 0).  Chunk 0 runs at full width with accumulate = 0: it zeroes the accumulators.
+                    int nb0 = 0, nbl = kTcN / 8;
+                    if (q > 0) {
+                        int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
+                        if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
+                        nb0 = lo;
+                        nbl = hi - lo + 1;
+                    }
+                    const uint32_t toff = (52 - 2 * q + nb0) * 128;
                     const uint64_t b0 = make_desc(t0 + toff, 128, 128), b1 = make_desc(t1 + toff, 128, 128);
                     const uint64_t b2 = make_desc(t2 + toff, 128, 128);
-                    const uint32_t acc = q > 0;
+                    const uint32_t acc = q > 0, idesc = make_idesc(8 * nbl);
+                    const uint32_t dE = tmem_base + kColE + 8 * nb0, dX = tmem_base + kColX + 8 * nb0;
                     if (!(p.dbg & 1)) {
-                        umma(tmem_base + kColE, a0, b0, idesc_main, acc);   // exact: integers < 2^24
-                        umma(tmem_base + kColX, a0, b1, idesc_main, acc);
-                        umma(tmem_base + kColX, a0, b2, idesc_main, 1);
-                        umma(tmem_base + kColX, a1, b0, idesc_main, 1);
-                        umma(tmem_base + kColX, a1, b1, idesc_main, 1);
+                        umma(dE, a0, b0, idesc, acc);   // exact: integers < 2^24
+                        umma(dX, a0, b1, idesc, acc);
+                        umma(dX, a0, b2, idesc, 1);
+                        umma(dX, a1, b0, idesc, 1);
+                        umma(dX, a1, b1, idesc, 1);
                     }
                     umma_commit(&cvt_empty[s]);  // frees the A stage when these MMAs have read it
                     w_i += clk() - c1;
@@ -472,7 +502,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const unsigned char *src = raw + rs * kRawStageBytes + cw * 2048;
             unsigned char *dst = cvt + cs * kCvtStageBytes;
 #pragma unroll
-            for (int kb = 0; kb < 2; kb++) {
+            for (int kb = 0; kb < ((p.dbg & 4) ? 0 : 2); kb++) {
                 const int row = 8 * kb + fr_i;
                 // SWIZZLE_128B: 16 B chunk c of a row lives at chunk position c ^ (row % 8)
                 const float4 va = *reinterpret_cast<const float4 *>(src + row * 128 + (((2 * mbq) ^ fr_i) << 4));
@@ -517,13 +547,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             pr[kProfCvtWaitCvt] = w_c;
             pr[kProfCvtWork] = w_w;
         }
-    } else if (warp < 14) {
+    } else if (warp < 18) {
         // ================================ biquad warps ================================
-        // warp e owns TMEM lanes [32e, 32e+32) == channels cg*128 + 32e + lane: an independent chain.
+        // Two warps per TMEM lane quadrant e (channels cg*128 + 32e + lane): role A (warps 10-13) drains rows [0,64)
+        // and runs chains 0,1 (rows 0-95) and the look-back; role B (warps 14-17) drains rows [64,128) and runs chains
+        // 2,3 (rows 96-175), then continues A's state chain (q2 arrives through a 16 B slot of the staging tile).
         const int e = warp & 3;
+        const bool roleB = warp >= 14;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
         unsigned char *stf = stage + e * 4 * kMbStride + lane * 4;                        // f32 view: + chunk + f32_off(r16)
         unsigned char *stp = stage + (e * 4 + (lane >> 3)) * kMbStride + (lane & 7) * 2;  // piece view: + chunk + piece + kb + fr*16
+        // never touched by the f32 view, the pieces or the MMA: the 16 B pad of core-matrix column 4e+3 of block `lane`
+        double2 *q2slot = reinterpret_cast<double2 *>(stage + (lane >> 2) * kChunkBytes + ((lane >> 1) & 1) * kPieceBytes +
+                                                      (lane & 1) * kKbStride + (e * 4 + 3) * kMbStride + 128);
         const BqCoef kc = {p.b0, p.b1, p.b2, -p.a1, -p.a2, p.ysc};
         float vmax = 0.f;
         long long e_w = 0, e_d = 0, e_z = 0, e_l = 0, e_m = 0;
@@ -540,23 +576,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const long long k1 = clk();
             e_w += k1 - k0;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            // ---- drain rows [0,80): FIR = (E + X) * descale into the staging tile; the look-back aggregate
+            // ---- drain 64 rows: FIR = (E + X) * descale into the staging tile; the look-back aggregate
             //      Z = sum_r W[159-r] fir[r] is accumulated on the way (16-term float partial sums folded in double)
             double Z0 = 0.0, Z1 = 0.0;
             const bool chained = !first && !last;
+            const int cbase = roleB ? kTcDrainB : 0;
 #pragma unroll
-            for (int c0 = 0; c0 < kTcSplit; c0 += 16) {
+            for (int cc = 0; cc < kTcDrainB; cc += 16) {
                 uint32_t re[16], rx[16];
-                tmem_ld16(tmem_base + lane_base + kColE + c0, re);
-                tmem_ld16(tmem_base + lane_base + kColX + c0, rx);
+                tmem_ld16(tmem_base + lane_base + kColE + cbase + cc, re);
+                tmem_ld16(tmem_base + lane_base + kColX + cbase + cc, rx);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float p0 = 0.f, p1 = 0.f;
+                unsigned char *dstc = stf + ((cbase + cc) >> 4) * kChunkBytes;
+                const float(*wf)[2] = p.Wf + (kTcFrames - 1 - (cbase + cc));
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const float v = (__uint_as_float(re[i]) + __uint_as_float(rx[i])) * p.descale_fir;
-                    *reinterpret_cast<float *>(stf + (c0 >> 4) * kChunkBytes + f32_off(i)) = v;
-                    p0 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][0], v, p0);
-                    p1 = fmaf(p.Wf[kTcFrames - 1 - (c0 + i)][1], v, p1);
+                    *reinterpret_cast<float *>(dstc + f32_off(i)) = v;
+                    p0 = fmaf(wf[-i][0], v, p0);
+                    p1 = fmaf(wf[-i][1], v, p1);
                 }
                 Z0 += (double)p0;
                 Z1 += (double)p1;
@@ -564,14 +603,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
+            if (roleB) {
+                zpart[e * 32 + lane] = make_double2(Z0, Z1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&zb_ready[e]);
+            }
             const long long k2 = clk();
             e_d += k2 - k1;
-            mbar_wait(&zb_ready[e], par);  // also orders this warp after the other half of the drain
+            mbar_wait(&zb_ready[e], par);  // all rows of this quadrant are staged; both other Z parts are in zpart
             const size_t slot = (size_t)grp * p.n_tiles + t;
-            if (chained) {
-                const double2 zb = zpart[e * 32 + lane];
-                Z0 += zb.x;
-                Z1 += zb.y;
+            if (!roleB && chained) {
+                const double2 zb = zpart[e * 32 + lane], zo = zpart[128 + e * 32 + lane];
+                Z0 += zb.x + zo.x;
+                Z1 += zb.y + zo.y;
                 p.lb_agg[slot * 64 + lane * 2] = Z0;
                 p.lb_agg[slot * 64 + lane * 2 + 1] = Z1;
                 __syncwarp();
@@ -580,37 +624,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const long long k3 = clk();
             e_z += k3 - k2;
 
-            // ---- four interleaved recursions in double over half-chunks of 8 rows; y*2^11 is split into
+            // ---- two interleaved zero-state recursions in double over half-chunks of 8 rows; y*2^11 is split into
             //      its fp16 pieces over the FIR values it was computed from
-            double cs1[kBqChains] = {0.0, 0.0, 0.0, 0.0}, cs2[kBqChains] = {0.0, 0.0, 0.0, 0.0};
+            double cs1[2] = {0.0, 0.0}, cs2[2] = {0.0, 0.0};
             double s159_1 = 0.0, s159_2 = 0.0, e3_1 = 0.0, e3_2 = 0.0;
             const float *yh = p.yhist + c;
-            if (first) {
-                cs1[0] = p.bq_state[2 * c];
-                cs2[0] = p.bq_state[2 * c + 1];
-            }
-            {   // chains 0 and 1 are one half-chunk longer than chains 2 and 3: they take it first
-                const int g2[2] = {kBqHc0, kBqHc1};
-                if (first) bq_step<2, true>(stf, stp, g2, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
-                else bq_step<2, false>(stf, stp, g2, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
-            }
-#pragma unroll 1
-            for (int i = 0; i < kBqLen2; i++) {
-                const int g4[kBqChains] = {kBqHc0 + 1 + i, kBqHc1 + 1 + i, kBqHc2 + i, kBqHc3 + i};
-                if (first && i == 0) bq_step<kBqChains, true>(stf, stp, g4, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
-                else bq_step<kBqChains, false>(stf, stp, g4, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
-                if (i == 2) {  // chain 3 after row 159: the state the next tile's row 0 starts from
-                    s159_1 = cs1[3];
-                    s159_2 = cs2[3];
+            if (!roleB) {
+                if (first) {
+                    cs1[0] = p.bq_state[2 * c];
+                    cs2[0] = p.bq_state[2 * c + 1];
                 }
-            }
-            if (last) {
-                // carried y history rows 160..174, zero-state part (the state response is added below), read back
-                // from the pieces just written: y * 2^11 = y0 + y1
-                for (int r = 0; r < kTcHr; r++) {
-                    const unsigned char *d = stp + 10 * kChunkBytes + (r >> 3) * kKbStride + (r & 7) * 16;
-                    const float v = __half2float(*reinterpret_cast<const __half *>(d)) + __half2float(*reinterpret_cast<const __half *>(d + kPieceBytes));
-                    p.yhist_next[(size_t)r * p.C + c] = v / p.yh_scale;
+#pragma unroll 1
+                for (int i = 0; i < kBqLen0; i++) {
+                    const int g2[2] = {kBqHc0 + i, kBqHc1 + i};
+                    if (first && i < 2) bq_step<2, true, false>(stf, stp, g2, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
+                    else bq_step<2, false, false>(stf, stp, g2, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
+                }
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < kBqLen2; i++) {
+                    const int g2[2] = {kBqHc2 + i, kBqHc3 + i};
+                    bq_step<2, false, true>(stf, stp, g2, kc, cs1, cs2, e3_1, e3_2, vmax, yh, p.C, p.yh_scale);
+                    if (i == 2) {  // chain 3 after row 159: the state the next tile's row 0 starts from
+                        s159_1 = cs1[1];
+                        s159_2 = cs2[1];
+                    }
+                }
+                if (last) {
+                    // carried y history rows 160..174, zero-state part (the state response is added below), read back
+                    // from the pieces just written: y * 2^11 = y0 + y1
+                    for (int r = 0; r < kTcHr; r++) {
+                        const unsigned char *d = stp + 10 * kChunkBytes + (r >> 3) * kKbStride + (r & 7) * 16;
+                        const float v = __half2float(*reinterpret_cast<const __half *>(d)) + __half2float(*reinterpret_cast<const __half *>(d + kPieceBytes));
+                        p.yhist_next[(size_t)r * p.C + c] = v / p.yh_scale;
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
@@ -619,111 +666,125 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const long long k4 = clk();
             e_m += k4 - k3;
 
-            // ---- incoming state: decoupled look-back (same protocol and arrays as K1, 32-channel groups)
-            double s1 = 0.0, s2 = 0.0;
-            if (!first) {
-                const int base = t - 1, j = base - lane;
-                int first_inc = 0;
-                for (unsigned spins = 0;; spins++) {
-                    unsigned stt = kLbInc;
-                    if (j >= 0) {
-                        stt = ld_acquire_u32(p.lb_status + (size_t)grp * p.n_tiles + j);
-                        stt = ((stt >> 2) == p.epoch) ? (stt & 3u) : kLbNone;
-                    }
-                    const unsigned ready = __ballot_sync(0xffffffffu, stt != kLbNone);
-                    const unsigned inc = __ballot_sync(0xffffffffu, stt == kLbInc);
-                    if (inc) {
-                        first_inc = __ffs(inc) - 1;
-                        const unsigned need = (first_inc == 0) ? 0u : (0xffffffffu >> (32 - first_inc));
-                        if ((ready & need) == need) break;
-                    }
-                    if (spins > (1u << 24)) {
-                        if (lane == 0) atomicExch(p.err_flag, 1);
-                        first_inc = -1;
-                        break;
-                    }
-                    __nanosleep(20);
-                }
-                __syncwarp();
-                const size_t s_inc = (size_t)grp * p.n_tiles + (first_inc < 0 ? 0 : base - first_inc);
-                s1 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2);
-                s2 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2 + 1);
-                // Horner over the aggregates between that inclusive state and this tile; payloads are fetched
-                // sixteen at a time so that only one L2 round trip per batch is exposed
-                for (int i0 = first_inc - 1; i0 >= 0; i0 -= 16) {
-                    double a0[16], a1[16];
-#pragma unroll
-                    for (int u = 0; u < 16; u++) {
-                        const int i = i0 - u;
-                        const size_t sa = (size_t)grp * p.n_tiles + (base - (i >= 0 ? i : 0));
-                        a0[u] = ld_cg(p.lb_agg + sa * 64 + lane * 2);
-                        a1[u] = ld_cg(p.lb_agg + sa * 64 + lane * 2 + 1);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 16; u++)
-                        if (i0 - u >= 0) {
-                            mat2_apply(p.AL, s1, s2);
-                            s1 += a0[u];
-                            s2 += a1[u];
+            if (!roleB) {
+                // ---- incoming state: decoupled look-back (same protocol and arrays as K1, 32-channel groups)
+                double s1 = 0.0, s2 = 0.0;
+                if (!first) {
+                    const int base = t - 1, j = base - lane;
+                    int first_inc = 0;
+                    for (unsigned spins = 0;; spins++) {
+                        unsigned stt = kLbInc;
+                        if (j >= 0) {
+                            stt = ld_acquire_u32(p.lb_status + (size_t)grp * p.n_tiles + j);
+                            stt = ((stt >> 2) == p.epoch) ? (stt & 3u) : kLbNone;
                         }
+                        const unsigned ready = __ballot_sync(0xffffffffu, stt != kLbNone);
+                        const unsigned inc = __ballot_sync(0xffffffffu, stt == kLbInc);
+                        if (inc) {
+                            first_inc = __ffs(inc) - 1;
+                            const unsigned need = (first_inc == 0) ? 0u : (0xffffffffu >> (32 - first_inc));
+                            if ((ready & need) == need) break;
+                        }
+                        if (spins > (1u << 24)) {
+                            if (lane == 0) atomicExch(p.err_flag, 1);
+                            first_inc = -1;
+                            break;
+                        }
+                        __nanosleep(20);
+                    }
+                    __syncwarp();
+                    const size_t s_inc = (size_t)grp * p.n_tiles + (first_inc < 0 ? 0 : base - first_inc);
+                    s1 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2);
+                    s2 = ld_cg(p.lb_inc + s_inc * 64 + lane * 2 + 1);
+                    // Horner over the aggregates between that inclusive state and this tile; payloads are fetched
+                    // eight at a time so that only one L2 round trip per batch is exposed
+                    for (int i0 = first_inc - 1; i0 >= 0; i0 -= 8) {
+                        double a0[8], a1[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int i = i0 - u;
+                            const size_t sa = (size_t)grp * p.n_tiles + (base - (i >= 0 ? i : 0));
+                            a0[u] = ld_cg(p.lb_agg + sa * 64 + lane * 2);
+                            a1[u] = ld_cg(p.lb_agg + sa * 64 + lane * 2 + 1);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (i0 - u >= 0) {
+                                mat2_apply(p.AL, s1, s2);
+                                s1 += a0[u];
+                                s2 += a1[u];
+                            }
+                    }
                 }
-            }
-            // ---- true state at the start of every chain (chain 0 of tile 0 carried it itself: its entry is zero)
-            double q1[kBqChains], q2[kBqChains];
-            q1[0] = s1;
-            q2[0] = s2;
-#pragma unroll
-            for (int j = 1; j < kBqChains; j++) {
-                double u1 = q1[j - 1], u2 = q2[j - 1];
-                mat2_apply(j == 3 ? p.AP40 : p.AP48, u1, u2);
-                q1[j] = u1 + cs1[j - 1];
-                q2[j] = u2 + cs2[j - 1];
-            }
-            if (!last) {
-                // inclusive state after row 159 (== before the next tile's row 0)
-                double I0 = q1[3], I1 = q2[3];
-                mat2_apply(p.AP24, I0, I1);
-                I0 += s159_1;
-                I1 += s159_2;
-                p.lb_inc[slot * 64 + lane * 2] = I0;
-                p.lb_inc[slot * 64 + lane * 2 + 1] = I1;
+                // ---- true state at the start of chains 0..2 (chain 0 of tile 0 carried it itself: its entry is zero)
+                double u1 = s1, u2 = s2;
+                mat2_apply(p.AP48, u1, u2);
+                const double q11 = u1 + cs1[0], q12 = u2 + cs2[0];
+                u1 = q11;
+                u2 = q12;
+                mat2_apply(p.AP48, u1, u2);
+                *q2slot = make_double2(u1 + cs1[1], u2 + cs2[1]);
+                sstate[(e * 8 + 0) * 32 + lane] = (float)s1;
+                sstate[(e * 8 + 1) * 32 + lane] = (float)s2;
+                sstate[(e * 8 + 2) * 32 + lane] = (float)q11;
+                sstate[(e * 8 + 3) * 32 + lane] = (float)q12;
                 __syncwarp();
-                if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
-            }
-#pragma unroll
-            for (int j = 0; j < kBqChains; j++) {
-                sstate[(e * 8 + 2 * j) * 32 + lane] = (float)q1[j];
-                sstate[(e * 8 + 2 * j + 1) * 32 + lane] = (float)q2[j];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&state_ready[e]);
-            if (last) {
-                // carried state: after row 174; carried y history: rows 160..174 with the state response added
-                double E0 = q1[3], E1 = q2[3];
-                mat2_apply(p.AP39, E0, E1);
-                p.bq_state_next[2 * c] = E0 + e3_1;
-                p.bq_state_next[2 * c + 1] = E1 + e3_2;
-                double u1 = q1[3], u2 = q2[3];
-                mat2_apply(p.AP24, u1, u2);
-                const double A[4] = {-p.a1, 1.0, -p.a2, 0.0};
-                for (int r = 0; r < kTcHr; r++) {
-                    float *hp = p.yhist_next + (size_t)r * p.C + c;
-                    *hp = (float)((double)*hp + u1 * p.g_bq);
-                    mat2_apply(A, u1, u2);
+                if (lane == 0) {
+                    mbar_arrive(&q2_ready[e]);
+                    mbar_arrive(&state_ready[e]);
+                }
+            } else {
+                mbar_wait(&q2_ready[e], par);
+                const double2 q2 = *q2slot;
+                double q31 = q2.x, q32 = q2.y;
+                mat2_apply(p.AP40, q31, q32);
+                q31 += cs1[0];
+                q32 += cs2[0];
+                if (!last) {
+                    // inclusive state after row 159 (== before the next tile's row 0)
+                    double I0 = q31, I1 = q32;
+                    mat2_apply(p.AP24, I0, I1);
+                    I0 += s159_1;
+                    I1 += s159_2;
+                    p.lb_inc[slot * 64 + lane * 2] = I0;
+                    p.lb_inc[slot * 64 + lane * 2 + 1] = I1;
+                    __syncwarp();
+                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
+                }
+                sstate[(e * 8 + 4) * 32 + lane] = (float)q2.x;
+                sstate[(e * 8 + 5) * 32 + lane] = (float)q2.y;
+                sstate[(e * 8 + 6) * 32 + lane] = (float)q31;
+                sstate[(e * 8 + 7) * 32 + lane] = (float)q32;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&state_ready[e]);
+                if (last) {
+                    // carried state: after row 174; carried y history: rows 160..174 with the state response added
+                    double E0 = q31, E1 = q32;
+                    mat2_apply(p.AP39, E0, E1);
+                    p.bq_state_next[2 * c] = E0 + e3_1;
+                    p.bq_state_next[2 * c + 1] = E1 + e3_2;
+                    double u1 = q31, u2 = q32;
+                    mat2_apply(p.AP24, u1, u2);
+                    const double A[4] = {-p.a1, 1.0, -p.a2, 0.0};
+                    for (int r = 0; r < kTcHr; r++) {
+                        float *hp = p.yhist_next + (size_t)r * p.C + c;
+                        *hp = (float)((double)*hp + u1 * p.g_bq);
+                        mat2_apply(A, u1, u2);
+                    }
                 }
             }
             e_l += clk() - k4;
         }
         if (vmax > 60000.f) atomicExch(p.err_flag, 2);
-        if (p.prof && warp == 10 && lane == 0) {
-            long long *pr = p.prof + blockIdx.x * kProfCount;
+        if (p.prof && (warp == 10 || warp == 14) && lane == 0) {
+            long long *pr = p.prof + blockIdx.x * kProfCount + (roleB ? kProfBWaitTmem - kProfBqWaitTmem : 0);
             pr[kProfBqWaitTmem] = e_w;
             pr[kProfBqDrain] = e_d;
             pr[kProfBqZ] = e_z;
             pr[kProfBqMain] = e_m;
             pr[kProfBqLookback] = e_l;
         }
-    } else if (warp < 18) {
+    } else if (warp < 22) {
         // ================================ output warps ================================
         const int e = warp & 3;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
@@ -738,10 +799,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_wait(tmem_full, par);
             if (it > 0) mbar_wait(stage_free, par ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            // ---- drain rows [80,176) with this warp's half of Z (rows [80,160)) accumulated on the way
+            // ---- drain rows [128,176) with this warp's part of Z (rows [128,160)) accumulated on the way
             double Z0 = 0.0, Z1 = 0.0;
 #pragma unroll
-            for (int c0 = kTcSplit; c0 < kTcN; c0 += 16) {
+            for (int c0 = 2 * kTcDrainB; c0 < kTcN; c0 += 16) {
                 uint32_t re[16], rx[16];
                 tmem_ld16(tmem_base + lane_base + kColE + c0, re);
                 tmem_ld16(tmem_base + lane_base + kColX + c0, rx);
@@ -762,7 +823,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
-            zpart[e * 32 + lane] = make_double2(Z0, Z1);
+            zpart[128 + e * 32 + lane] = make_double2(Z0, Z1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&zb_ready[e]);
 
@@ -780,30 +841,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 mbar_wait(&d2_full[b], (nsl >> 1) & 1u);
                 r_w += clk() - k6;
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                uint32_t re[32], rx[32];
-                tmem_ld32(tmem_base + lane_base + kColD2 + 64 * b, re);
-                tmem_ld32(tmem_base + lane_base + kColD2 + 64 * b + 32, rx);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d2_empty[b]);
                 if (s == 0) {
                     mbar_wait(&state_ready[e], par);
 #pragma unroll
                     for (int q = 0; q < 8; q++) sv[q] = sstate[(e * 8 + q) * 32 + lane];
                 }
+                // the rows of this slice belong to chains (j, j+1): four state components matter
+                const float q0 = s < 2 ? sv[0] : (s == 2 ? sv[2] : sv[4]), q1 = s < 2 ? sv[1] : (s == 2 ? sv[3] : sv[5]);
+                const float q2 = s < 2 ? sv[2] : (s == 2 ? sv[4] : sv[6]), q3 = s < 2 ? sv[3] : (s == 2 ? sv[5] : sv[7]);
 #pragma unroll
-                for (int i = 0; i < kRsN; i++) {
-                    const int m = kRsN * s + i;
-                    if (m < kTcOut) {
-                        float corr = 0.f;
+                for (int h = 0; h < 2; h++) {
+                    uint32_t re[16], rx[16];
+                    tmem_ld16(tmem_base + lane_base + kColD2 + 64 * b + 16 * h, re);
+                    tmem_ld16(tmem_base + lane_base + kColD2 + 64 * b + 32 + 16 * h, rx);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (h == 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&d2_empty[b]);
+                    }
 #pragma unroll
-                        for (int q = 0; q < 8; q++) corr = fmaf(p.rc[m][q], sv[q], corr);
-                        const float o = fmaf(__uint_as_float(re[i]) + __uint_as_float(rx[i]), p.descale_rs, corr);
-                        outp[(size_t)m * p.C] = o;
-                        if (meter) {
-                            m_peak = fmaxf(m_peak, fabsf(o));
-                            m_sumsq += (double)o * (double)o;
+                    for (int i = 0; i < 16; i++) {
+                        const int m = kRsN * s + 16 * h + i;
+                        if (m < kTcOut) {
+                            const float corr = fmaf(p.rc[m][0], q0, fmaf(p.rc[m][1], q1, fmaf(p.rc[m][2], q2, p.rc[m][3] * q3)));
+                            const float o = fmaf(__uint_as_float(re[i]) + __uint_as_float(rx[i]), p.descale_rs, corr);
+                            outp[(size_t)m * p.C] = o;
+                            if (meter) {
+                                m_peak = fmaxf(m_peak, fabsf(o));
+                                m_sumsq += (double)o * (double)o;
+                            }
                         }
                     }
                 }
@@ -814,7 +881,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 atomicAdd(p.meter_sumsq + c, m_sumsq);
             }
         }
-        if (p.prof && warp == 14 && lane == 0) {
+        if (p.prof && warp == 18 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
             pr[kProfOutWait] = r_w;
             pr[kProfOutMain] = r_m;
@@ -845,10 +912,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                         const uint64_t a0 = make_desc(a_base, kKbStride, kMbStride), a1 = make_desc(a_base + kPieceBytes, kKbStride, kMbStride);
                         const uint64_t r0 = make_desc(b2 + pair * 2048, 128, 256), r1 = make_desc(b2 + pair * 2048 + 1024, 128, 256);
                         const uint32_t acc = k > 0;
-                        umma(dE, a0, r0, idesc_rs, acc);   // exact: integers < 2^24
-                        umma(dX, a0, r1, idesc_rs, acc);
-                        umma(dX, a1, r0, idesc_rs, 1);
-                        umma(dX, a1, r1, idesc_rs, 1);
+                        if (!(p.dbg & 2)) {
+                            umma(dE, a0, r0, idesc_rs, acc);   // exact: integers < 2^24
+                            umma(dX, a0, r1, idesc_rs, acc);
+                            umma(dX, a1, r0, idesc_rs, 1);
+                            umma(dX, a1, r1, idesc_rs, 1);
+                        }
                     }
                     umma_commit(&d2_full[b]);
                 }
