@@ -47,10 +47,11 @@ struct Segment {
     void *d_tc_tables = nullptr;
     int tc_sh = 0;
     double tc_AL[4] = {1, 0, 0, 1};
-    double tc_W[2 * kTcFrames] = {0};
-    int tc_sh2 = 0;                                  // fixed-point shift of the resampler taps
-    double tc_AP48[4], tc_AP40[4], tc_AP24[4], tc_AP39[4];
-    std::vector<float> tc_rc;                        // [147][8] output correction per chain state (see chain_tc.cuh)
+    int tc_sh2 = 0;                                  // fixed-point shift of the folded biquad+resampler matrix P
+    double tc_A16[4], tc_ALf[4];                     // A^16, A^145
+    float tc_Wz[16][2];
+    float tc_Mb[2][kTcBlocks][4];
+    std::vector<float> tc_rc;                        // [147 + 32][8] output correction per block state (see chain_tc.cuh)
 };
 
 struct Slot {  // one in-flight batch of the pipelined host path
@@ -224,12 +225,8 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     const double B[2] = {s.b[1] - s.a[0] * s.b[0], s.b[2] - s.a[1] * s.b[0]};
     double M[4] = {1, 0, 0, 1};
     for (int k = 0; k <= kTcFrames; k++) {
-        if (k < kTcFrames) {
-            s.tc_W[2 * k] = M[0] * B[0] + M[1] * B[1];
-            s.tc_W[2 * k + 1] = M[2] * B[0] + M[3] * B[1];
-        } else {
+        if (k == kTcFrames)
             for (int i = 0; i < 4; i++) s.tc_AL[i] = M[i];
-        }
         const double N[4] = {M[0] * A[0] + M[1] * A[2], M[0] * A[1] + M[1] * A[3], M[2] * A[0] + M[3] * A[2],
                              M[2] * A[1] + M[3] * A[3]};
         for (int i = 0; i < 4; i++) M[i] = N[i];
@@ -245,52 +242,78 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 split_fixed3(gtap(8 * e + n_i - k_i + 1) * sh, T0[idx], T1[idx], T2[idx]);
             }
     PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    // MMA2: the polyphase matrix of one tile, R[row][m] = coef[branch(m)][i_m - row], row = frame + 15.
-    // Output m is triggered by tile-relative frame i_m = ceil((m+1)*160/147) - 1 with branch 146 - ((i_m+1)*147 % 160).
-    // Slice s (outputs [32s, 32s+32)) reads row chunks [2s, 2s+4) (the last slice 3): 19 blocks [32 outputs][16 rows],
-    // K-major 8x8 core matrices, two fp16 pieces on the fixed grid 2^sh2.
+    // MMA2: P = blockdiag(G16) * R.  R[row][m] = coef[branch(m)][i_m - row] is the polyphase matrix of one tile (row = frame + 15;
+    // output m is triggered by tile-relative frame i_m = ceil((m+1)*160/147) - 1 with branch 146 - ((i_m+1)*147 % 160)); G16 is the
+    // biquad's zero-state response inside a block of 16 rows: y[r'] = sum_{r <= r', same block} g[r'-r] f[r], g[0] = b0,
+    // g[k] = (A^(k-1) B)[0].  So P[row][m] = sum_{r' = row .. end of row's block} R[r'][m] g[r'-row].
+    // Slice s (outputs [32s, 32s+32)) reads row blocks [2s, 2s+4) (the last slice 3): 19 blocks [32 outputs][16 rows], K-major 8x8
+    // core matrices, two fp16 pieces on the fixed grid 2^sh2, the two pieces of a block adjacent ([p0 | p1] is one N = 64 operand).
+    // Entry 19 is block (0, 0) for tile 0: rows 0..14 are the carried y history (plain R, no biquad), row 15 starts the recursion.
     const auto &rs = c->stages[s.rs_stage];
     auto rtap = [&](int row, int m) -> double {
-        if (m >= kTcOut) return 0.0;
+        if (m >= kTcOut || row < 0 || row >= kTcN) return 0.0;
         const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1;
         const int k = im + kTcHr - row;
         if (k < 0 || k >= kTcP) return 0.0;
         const int br = kTcUp - 1 - (((im + 1) * kTcUp) % kTcFrames);
         return rs.taps[(size_t)br + (size_t)k * kTcUp];
     };
+    double g[16], Apow[kTcN + 1][4];
     {
-        std::vector<double> all;
-        for (int m = 0; m < kTcOut; m++) {
-            double sum = 0;  // the grid must keep sum|r0| of ONE output below 8191
-            for (int row = 0; row < kTcN; row++) sum += std::fabs(rtap(row, m));
-            all.push_back(sum);
+        double Mk[4] = {1, 0, 0, 1};
+        for (int k = 0; k <= kTcN; k++) {
+            for (int i = 0; i < 4; i++) Apow[k][i] = Mk[i];
+            const double N[4] = {Mk[0] * A[0] + Mk[1] * A[2], Mk[0] * A[1] + Mk[1] * A[3], Mk[2] * A[0] + Mk[3] * A[2],
+                                 Mk[2] * A[1] + Mk[3] * A[3]};
+            for (int i = 0; i < 4; i++) Mk[i] = N[i];
         }
+        g[0] = s.b[0];
+        for (int k = 1; k < 16; k++) g[k] = Apow[k - 1][0] * B[0] + Apow[k - 1][1] * B[1];
+    }
+    // first0: the tile-0 variant of block 0
+    auto ptap = [&](int row, int m, bool first0) -> double {
+        if (first0 && row < kTcHr) return rtap(row, m);
+        const int end = (row / 16) * 16 + 15;
+        double v = 0;
+        for (int rp = row; rp <= end && rp < kTcN; rp++) v += rtap(rp, m) * g[rp - row];
+        return v;
+    };
+    {
         double mx = 0, smax = 0;
-        for (size_t i = 0; i < rs.taps.size(); i++) mx = std::max(mx, std::fabs(rs.taps[i]));
-        for (double v : all) smax = std::max(smax, v);
+        for (int f0 = 0; f0 < 2; f0++)
+            for (int m = 0; m < kTcOut; m++) {
+                double sum = 0;  // the grid must keep sum|p0| of ONE output below 8191
+                for (int row = 0; row < kTcN; row++) {
+                    const double v = std::fabs(ptap(row, m, f0 && row < 16));
+                    sum += v;
+                    mx = std::max(mx, v);
+                }
+                smax = std::max(smax, sum);
+            }
         int sh2 = 0;
         if (mx > 0) sh2 = (int)std::floor(std::log2(std::min(2047.0 / mx, 8191.0 / smax)));
         s.tc_sh2 = std::max(-24, std::min(24, sh2));
     }
     const double sh2 = std::ldexp(1.0, s.tc_sh2);
     std::vector<__half> b2((size_t)TcTables::kB2);
+    auto fill_pair = [&](int pair, int sl, int chunk, bool first0) {
+        for (int n = 0; n < kRsN; n++)
+            for (int kk = 0; kk < 16; kk++) {
+                const double v = ptap(16 * chunk + kk, kRsN * sl + n, first0) * sh2;
+                const size_t idx = (size_t)(n / 8) * 128 + (size_t)(kk / 8) * 64 + (size_t)(n % 8) * 8 + (size_t)(kk % 8);
+                __half r0 = __float2half_rn((float)std::nearbyint(v));
+                __half r1 = __float2half_rn((float)(v - (double)__half2float(r0)));
+                b2[(size_t)pair * 1024 + idx] = r0;
+                b2[(size_t)pair * 1024 + 512 + idx] = r1;
+            }
+    };
     int pair = 0;
     for (int sl = 0; sl < kRsSlices; sl++) {
         const int nch = (sl == kRsSlices - 1) ? 3 : 4;
-        for (int k = 0; k < nch; k++, pair++) {
-            const int chunk = 2 * sl + k;
-            for (int n = 0; n < kRsN; n++)
-                for (int kk = 0; kk < 16; kk++) {
-                    const double v = rtap(16 * chunk + kk, kRsN * sl + n) * sh2;
-                    const size_t idx = (size_t)(n / 8) * 128 + (size_t)(kk / 8) * 64 + (size_t)(n % 8) * 8 + (size_t)(kk % 8);
-                    __half r0 = __float2half_rn((float)std::nearbyint(v));
-                    __half r1 = __float2half_rn((float)(v - (double)__half2float(r0)));
-                    b2[(size_t)pair * 1024 + idx] = r0;
-                    b2[(size_t)pair * 1024 + 512 + idx] = r1;
-                }
-        }
+        for (int k = 0; k < nch; k++, pair++) fill_pair(pair, sl, 2 * sl + k, false);
     }
-    // every tap of every output must be inside the chunks its slice reads
+    fill_pair(kRsPairs, 0, 0, true);
+    // every tap of every output must be inside the blocks its slice reads
     for (int m = 0; m < kTcOut; m++) {
         const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1, sl = m / kRsN;
         const int lo = im, hi = im + kTcHr, nch = (sl == kRsSlices - 1) ? 3 : 4;
@@ -298,49 +321,46 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     }
     PB_CUDA(cudaMemcpy((char *)s.d_tc_tables + (size_t)TcTables::kHalfs * 2, b2.data(), b2.size() * sizeof(__half),
                        cudaMemcpyHostToDevice));
-    // Biquad chains (rows 0-47, 48-95, 96-135, 136-175) run from a zero state; the response of output m to the true
-    // state q(j) at the start of chain j is rc[m][2j..2j+1] = g_bq g_out sum_{rows r of chain j} R[r][m] (A^(r-start_j))[0][.]
+    // Block states.  The response of output m to the true state at the start of block b is
+    //   rc[m][2k..2k+1] = g_bq g_out sum_{rows r of block b} R[r][m] (A^(r-16b))[0][.],   b = 2 (m/32) + k, k = 0..3;
+    // tile 0, block 0: the state enters at row 15.
     {
-        const int start[kBqChains + 1] = {8 * kBqHc0, 8 * kBqHc1, 8 * kBqHc2, 8 * kBqHc3, kTcN};
-        std::vector<double> acc((size_t)kTcOut * 8, 0.0);
-        for (int j = 0; j < kBqChains; j++) {
-            double Mk[4] = {1, 0, 0, 1};
-            for (int row = start[j]; row < start[j + 1]; row++) {
-                for (int m = 0; m < kTcOut; m++) {
-                    const double r = rtap(row, m);
-                    if (r != 0.0) {
-                        acc[(size_t)m * 8 + 2 * j] += r * Mk[0];
-                        acc[(size_t)m * 8 + 2 * j + 1] += r * Mk[1];
-                    }
+        const double gg = s.g[2] * s.g[3];
+        s.tc_rc.assign((size_t)(kTcOut + kRsN) * 8, 0.f);
+        for (int m = 0; m < kTcOut; m++)
+            for (int b = 0; b < kTcBlocks; b++) {
+                double v0 = 0, v1 = 0;
+                for (int i = 0; i < 16; i++) {
+                    const double r = rtap(16 * b + i, m);
+                    v0 += r * Apow[i][0];
+                    v1 += r * Apow[i][1];
                 }
-                const double N[4] = {Mk[0] * A[0] + Mk[1] * A[2], Mk[0] * A[1] + Mk[1] * A[3], Mk[2] * A[0] + Mk[3] * A[2],
-                                     Mk[2] * A[1] + Mk[3] * A[3]};
-                for (int i = 0; i < 4; i++) Mk[i] = N[i];
-            }
-        }
-        s.tc_rc.assign((size_t)kTcOut * 4, 0.f);
-        for (int m = 0; m < kTcOut; m++) {
-            const int j0 = rs_chain_of_slice(m / kRsN);
-            for (int j = 0; j < kBqChains; j++)
-                for (int q = 0; q < 2; q++) {
-                    const double v = acc[(size_t)m * 8 + 2 * j + q] * s.g[2] * s.g[3];
-                    if (j == j0 || j == j0 + 1) s.tc_rc[(size_t)m * 4 + 2 * (j - j0) + q] = (float)v;
-                    else if (v != 0.0) return fail(PB_ERR_UNSUPPORTED, "resampler output %d reads rows outside its two biquad chains", m);
+                const int k = b - 2 * (m / kRsN);
+                if (k >= 0 && k < 4) {
+                    s.tc_rc[(size_t)m * 8 + 2 * k] = (float)(v0 * gg);
+                    s.tc_rc[(size_t)m * 8 + 2 * k + 1] = (float)(v1 * gg);
+                } else if (v0 != 0.0 || v1 != 0.0) {
+                    return fail(PB_ERR_UNSUPPORTED, "resampler output %d reads rows outside the blocks of its slice", m);
                 }
-        }
-        auto mpow = [&](int n, double *out) {
-            double Mk[4] = {1, 0, 0, 1};
-            for (int k = 0; k < n; k++) {
-                const double N[4] = {Mk[0] * A[0] + Mk[1] * A[2], Mk[0] * A[1] + Mk[1] * A[3], Mk[2] * A[0] + Mk[3] * A[2],
-                                     Mk[2] * A[1] + Mk[3] * A[3]};
-                for (int i = 0; i < 4; i++) Mk[i] = N[i];
             }
-            for (int i = 0; i < 4; i++) out[i] = Mk[i];
-        };
-        mpow(48, s.tc_AP48);
-        mpow(40, s.tc_AP40);
-        mpow(24, s.tc_AP24);
-        mpow(39, s.tc_AP39);
+        for (int m = 0; m < kRsN; m++) {
+            for (int q = 0; q < 8; q++) s.tc_rc[(size_t)(kTcOut + m) * 8 + q] = s.tc_rc[(size_t)m * 8 + q];
+            s.tc_rc[(size_t)(kTcOut + m) * 8 + 0] = (float)(rtap(kTcHr, m) * gg);  // block 0: only row 15, (A^0)[0] = [1 0]
+            s.tc_rc[(size_t)(kTcOut + m) * 8 + 1] = 0.f;
+        }
+        for (int b = 0; b < kTcBlocks; b++)
+            for (int i = 0; i < 4; i++) {
+                s.tc_Mb[0][b][i] = (float)Apow[16 * b][i];
+                s.tc_Mb[1][b][i] = (float)(b == 0 ? (i == 0 || i == 3 ? 1.0 : 0.0) : Apow[16 * b - kTcHr][i]);
+            }
+        for (int i = 0; i < 4; i++) {
+            s.tc_A16[i] = Apow[16][i];
+            s.tc_ALf[i] = Apow[kTcFrames - kTcHr][i];
+        }
+        for (int i = 0; i < 16; i++) {
+            s.tc_Wz[i][0] = (float)((Apow[15 - i][0] * B[0] + Apow[15 - i][1] * B[1]) / 1024.0);
+            s.tc_Wz[i][1] = (float)((Apow[15 - i][2] * B[0] + Apow[15 - i][3] * B[1]) / 1024.0);
+        }
     }
     return PB_OK;
 }
@@ -424,24 +444,21 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     p.scale_in = (float)(s.g[0] * sx);
     p.scale_hist = (float)sx;
     p.inv_scale_in = (float)(1.0 / sx);
-    p.descale_fir = (float)(s.g[1] / (sx * std::ldexp(1.0, s.tc_sh)));
-    p.descale_rs = (float)(s.g[3] / (sx * std::ldexp(1.0, s.tc_sh2)));
-    p.yh_scale = (float)sx;
+    const double sf = 1024.0;  // grid of the FIR output pieces
+    p.fscale = (float)(s.g[1] * sf / (sx * std::ldexp(1.0, s.tc_sh)));
+    p.inv_fgrid = (float)(1.0 / sf);
+    p.yh_scale = (float)(sf / s.g[2]);
+    p.descale_rs = (float)(s.g[2] * s.g[3] / (sf * std::ldexp(1.0, s.tc_sh2)));
     p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
     p.g_bq = s.g[2];
-    p.ysc = s.g[2] * sx * 8192.0;
     for (int i = 0; i < 4; i++) {
         p.AL[i] = s.tc_AL[i];
-        p.AP48[i] = s.tc_AP48[i];
-        p.AP40[i] = s.tc_AP40[i];
-        p.AP24[i] = s.tc_AP24[i];
-        p.AP39[i] = s.tc_AP39[i];
+        p.AL_first[i] = s.tc_ALf[i];
+        p.A16[i] = s.tc_A16[i];
     }
+    memcpy(p.Wz, s.tc_Wz, sizeof(p.Wz));
+    memcpy(p.Mb, s.tc_Mb, sizeof(p.Mb));
     memcpy(p.rc, s.tc_rc.data(), sizeof(p.rc));
-    for (int k = 0; k < kTcFrames; k++) {
-        p.Wf[k][0] = (float)s.tc_W[2 * k];
-        p.Wf[k][1] = (float)s.tc_W[2 * k + 1];
-    }
     if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int total = p.n_tiles * p.n_cg;
     const int grid = std::min(total, c->num_sms);
@@ -463,12 +480,11 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         PB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_prof);
         static const char *names[] = {"prod_wait_empty", "mma_wait_tmem", "mma_wait_cvt", "mma_issue", "cvt_wait_raw",
-                                      "cvt_wait_cvt", "cvt_work", "bq_wait_tmem", "bq_drain", "bq_zpass", "bq_main",
-                                      "bq_lookback", "total", "out_wait_d2", "out_main", "mma2_wait_y", "bqB_wait_tmem",
-                                      "bqB_drain", "bqB_wait_z", "bqB_main", "bqB_state"};
+                                      "cvt_wait_cvt", "cvt_work", "drain_wait_blk", "drain_work", "drain_lookback", "total",
+                                      "out_wait", "out_main", "mma2_wait_a2"};
         const double tiles_per_cta = (double)total / grid;
         fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
-        for (int k = 0; k <= tc::kProfBLookback; k++) {
+        for (int k = 0; k <= tc::kProfMma2Wait; k++) {
             double sum = 0;
             for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + k];
             fprintf(stderr, "  %-16s %10.0f\n", names[k], sum / grid / tiles_per_cta);
@@ -725,7 +741,7 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
             const bool lastseg = (i + 1 == c->segs.size());
             void *dst = lastseg ? out_dev : c->d_mid[i & 1];
             // K2 needs the call aligned to 160-frame tiles (then the resampler phase is 0 at every tile start)
-            const bool use_tc = s.tc_ok && s.acc == 0 && n >= kTcFrames && n % kTcFrames == 0 &&
+            const bool use_tc = s.tc_ok && s.acc == 0 && n >= kTcFrames && n % kTcFrames == 0 && s.g[2] != 0.0 && s.b[0] == s.b[0] &&
                                 ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
             int32_t r = use_tc ? launch_segment_tc(c, s, src, n, dst, lastseg, stream)
                         : c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, src, n, dst, lastseg, stream)
