@@ -45,6 +45,7 @@ struct Segment {
     // K2 (tcgen05 path): eligibility, fp16 tables, fixed-point shifts, A^160
     bool tc_ok = false;
     void *d_tc_tables = nullptr;
+    void *d_tc_rc = nullptr;
     int tc_sh = 0;
     double tc_AL[4] = {1, 0, 0, 1};
     int tc_sh2 = 0;                                  // fixed-point shift of the folded biquad+resampler matrix P
@@ -165,7 +166,7 @@ static void plan_segments(pb_chain *c)
 static void free_segment(Segment &s)
 {
     void *ptrs[] = {s.d_taps, s.d_wt, s.d_apow, s.d_coef, s.d_xhist[0], s.d_xhist[1], s.d_yhist[0], s.d_yhist[1],
-                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables};
+                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables, s.d_tc_rc};
     for (void *p : ptrs)
         if (p) cudaFree(p);
 }
@@ -326,7 +327,7 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     // tile 0, block 0: the state enters at row 15.
     {
         const double gg = s.g[2] * s.g[3];
-        s.tc_rc.assign((size_t)(kTcOut + kRsN) * 8, 0.f);
+        s.tc_rc.assign((size_t)kTcRcRows * 8, 0.f);
         for (int m = 0; m < kTcOut; m++)
             for (int b = 0; b < kTcBlocks; b++) {
                 double v0 = 0, v1 = 0;
@@ -344,10 +345,11 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 }
             }
         for (int m = 0; m < kRsN; m++) {
-            for (int q = 0; q < 8; q++) s.tc_rc[(size_t)(kTcOut + m) * 8 + q] = s.tc_rc[(size_t)m * 8 + q];
-            s.tc_rc[(size_t)(kTcOut + m) * 8 + 0] = (float)(rtap(kTcHr, m) * gg);  // block 0: only row 15, (A^0)[0] = [1 0]
-            s.tc_rc[(size_t)(kTcOut + m) * 8 + 1] = 0.f;
+            for (int q = 0; q < 8; q++) s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + q] = s.tc_rc[(size_t)m * 8 + q];
+            s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 0] = (float)(rtap(kTcHr, m) * gg);  // block 0: only row 15, (A^0)[0] = [1 0]
+            s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 1] = 0.f;
         }
+        PB_CUDA(cudaMemcpy(s.d_tc_rc, s.tc_rc.data(), s.tc_rc.size() * sizeof(float), cudaMemcpyHostToDevice));
         for (int b = 0; b < kTcBlocks; b++)
             for (int i = 0; i < 4; i++) {
                 s.tc_Mb[0][b][i] = (float)Apow[16 * b][i];
@@ -458,7 +460,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     }
     memcpy(p.Wz, s.tc_Wz, sizeof(p.Wz));
     memcpy(p.Mb, s.tc_Mb, sizeof(p.Mb));
-    memcpy(p.rc, s.tc_rc.data(), sizeof(p.rc));
+    p.rc = (const float *)s.d_tc_rc;
     if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int total = p.n_tiles * p.n_cg;
     const int grid = std::min(total, c->num_sms);
@@ -612,6 +614,7 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     }
     s.tc_ok = tc_shape_ok(c, s);
     if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_tables, (size_t)TcTables::kBytes));
+    if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_rc, (size_t)kTcRcRows * 8 * sizeof(float)));
     return refresh_segment_params(c, s);
 }
 

@@ -65,7 +65,7 @@ constexpr int kTcWin = kTcChunks * 16;
 constexpr int kTcLead = 272;        // frames of the window before the tile start
 constexpr int kTcMaxTaps = 257;
 constexpr int kTcCores = 75;        // Toeplitz core matrices per piece
-constexpr int kTcThreads = 608;     // 19 warps: TMA, MMA1, 2x4 converters, 4 drain, 4 output, MMA2
+constexpr int kTcThreads = 736;     // 23 warps: TMA, MMA1, 2x4 converters, 2x4 drain, 4 output, MMA2
 constexpr int kRawStages = 4, kCvtStages = 3;
 constexpr int kTcBlocks = kTcN / 16;     // 11 blocks of 16 rows: biquad blocks == K chunks of MMA2
 constexpr int kTcFirstDone = 17;    // column block b of D1 is complete after chunk b + 17 (the last two after chunk 26)
@@ -85,6 +85,7 @@ struct TcParams {
     CUtensorMap tm_hist;  // xhist [256][C] f32 (already gain-scaled), same box
     float *out;
     const __half *tables;
+    const float *rc;      // [kTcRcRows][8]
     const float *yhist;
     float *yhist_next;
     float *xhist_next;
@@ -113,8 +114,13 @@ struct TcParams {
     float Wz[16][2];     // zero-state end state of a block: Z = sum_i Wz[i] * f_i (on the grid), Wz[i] = A^(15-i) B / 2^10
     float Mb[2][kTcBlocks][4];     // [0]: A^(16 b), incoming state -> state at the start of block b;
                                    // [1]: tile 0: identity for b = 0 (the state enters at row 15), A^(16 b - 15) after
-    float rc[kTcOut + kRsN][8];    // out[m] += sum_k rc[m][2k..2k+1] . s(block 2*(m/32) + k); rows 147.. : tile 0, slice 0
 };
+
+// out[m] += sum_k rc[m][2k..2k+1] . s(block 2*(m/32) + k), k = 0..3; rows 147.. : tile 0, slice 0.  In global memory, copied at
+// kernel start into the 16 B pads of the staging tile's core-matrix slots (shared memory is full; kernel parameters would be
+// read with indexed constant loads, which bounded the output warps).
+constexpr int kTcRcFirst = 152;      // row of the tile-0 variant of slice 0 (a multiple of 8: the pad address of a row then splits into slice base + constant)
+constexpr int kTcRcRows = kTcRcFirst + kRsN;
 
 #ifdef __CUDACC__
 
@@ -200,6 +206,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t &r0, uint32_t &r1)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
@@ -239,11 +253,15 @@ constexpr int kStageBytes = kTcBlocks * kChunkBytes;            // 101376
 constexpr int kOffSstate = kOffStage + kStageBytes;             // [4][2][32] float: incoming state of the tile
 constexpr int kOffBar = kOffSstate + 4 * 2 * 32 * 4;
 constexpr int kNumBlkBars = kTcChunks - kTcFirstDone;           // 10: one per chunk 17..26
-constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + 1 + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4;
+constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + 1 + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 4;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
 static_assert(kOffStage % 16 == 0 && kChunkBytes % 16 == 0, "UMMA descriptor alignment");
+
+// byte offset (from the staging tile) of half h (4 floats) of row m of the rc table: pad 2m+h of the 704 pads
+__host__ __device__ constexpr int rc_pad_off(int m, int h) { return (m >> 3) * kKbStride + (2 * (m & 7) + h) * kMbStride + 128; }
+static_assert(rc_pad_off(kTcRcRows - 1, 1) + 16 <= kStageBytes, "rc table fits in the pads");
 
 // TMEM columns: D1 = E [0,176) + X [176,352); D2 double-buffered slices [E2 | X2] of 32 + 32 columns from 352;
 // mailbox of the 11 block states (2 columns each, 24 with padding) from 480
@@ -296,7 +314,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     uint64_t *d2_empty = d2_full + 2;               // [2]  output warps -> MMA2
     uint64_t *state_ready = d2_empty + 2;           // [4]  drain warp e -> output warp e: incoming state in sstate
     uint64_t *mbox_ready = state_ready + 4;         // [4]  drain warp e -> output warp e: block states in the TMEM mailbox
-    uint64_t *mbox_free = mbox_ready + 4;           // [4]  output warp e -> drain warp e
+    uint64_t *mbox_free = mbox_ready + 4;           // [4]  output warp e -> drain warps e
+    uint64_t *zx_ready = mbox_free + 4;             // [4]  drain warp B -> drain warp A: the Z of the odd blocks are in the mailbox
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmemSlot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -317,7 +336,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&cvt_empty[i], 1);
         }
         for (int i = 0; i < kNumBlkBars; i++) mbar_init(&blk_full[i], 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, 8);
         for (int i = 0; i < kTcBlocks; i++) mbar_init(&a2_ready[i], 4);
         mbar_init(stage_free, 1);
         for (int i = 0; i < 2; i++) {
@@ -328,6 +347,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&state_ready[i], 1);
             mbar_init(&mbox_ready[i], 1);
             mbar_init(&mbox_free[i], 1);
+            mbar_init(&zx_ready[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -336,6 +356,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
         for (int i = tid; i < kTabBytes / 16; i += kTcThreads) dst[i] = src[i];
     }
+    for (int i = tid; i < kTcRcRows * 2; i += kTcThreads)
+        *reinterpret_cast<float4 *>(stage + rc_pad_off(i >> 1, i & 1)) = reinterpret_cast<const float4 *>(p.rc)[i];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -384,6 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 mbar_wait(tmem_empty, tph ^ 1);  // the previous tile's D1 has been read
                 w_t += clk() - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll 1
                 for (int q = 0; q < kTcChunks; q++) {
                     c0 = clk();
                     mbar_wait(&cvt_full[s], ph);
@@ -504,12 +527,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             pr[kProfCvtWaitCvt] = w_c;
             pr[kProfCvtWork] = w_w;
         }
-    } else if (warp < 14) {
+    } else if (warp < 18) {
         // ================================ FIR drain warps =============================
-        // warp e owns TMEM lanes [32e, 32e+32) == channels cg*128 + 32e + lane.  Per block of 16 columns:
-        // f*2^10 = (E + X) * fscale -> fp16 pieces f0 (integer grid) + f1 into the A operand of MMA2, and the
-        // zero-state end state of the block Z_b (16-term float sums folded in double) into the block-state recursion.
+        // Two warps per TMEM lane quadrant e (channels cg*128 + 32e + lane): role A (warps 10-13) takes the even
+        // blocks of 16 columns, role B (warps 14-17) the odd ones.  Per block: f*2^10 = (E + X) * fscale -> fp16 pieces
+        // f0 (integer grid) + f1 into the A operand of MMA2, and the zero-state end state of the block Z_b (16-term float
+        // sums) into the TMEM mailbox.  Role A then runs the block-state recursion in double and the look-back.
         const int e = warp & 3;
+        const bool roleB = warp >= 14;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
         unsigned char *stp = stage + (e * 4 + (lane >> 3)) * kMbStride + (lane & 7) * 2;  // + chunk + piece + kb + fr*16
         float vmax = 0.f;
@@ -523,30 +548,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const uint32_t par = it & 1;
             const size_t slot = (size_t)grp * p.n_tiles + t;
             const bool chained = !first && !last;
-            if (it > 0) mbar_wait(stage_free, par ^ 1);  // MMA2 has consumed the previous tile's pieces
-            double s1 = 0.0, s2 = 0.0;                   // zero-state block recursion
-            double s10_1 = 0.0, s10_2 = 0.0;             // ... at the start of block 10 == after row 159
             const float *yh = p.yhist + c;
-            if (it > 0) mbar_wait(&mbox_free[e], par ^ 1);  // the output warp has read the previous tile's block states
-            long long k1 = 0;
+            if (it > 0) mbar_wait(stage_free, par ^ 1);  // MMA2 has consumed the previous tile's pieces
 #pragma unroll 1
-            for (int b = 0; b < kTcBlocks; b++) {
+            for (int b = roleB ? 1 : 0; b < kTcBlocks; b += 2) {
                 const long long k0 = clk();
-                if (b < kNumBlkBars) mbar_wait(&blk_full[b], par);
-                k1 = clk();
+                mbar_wait(&blk_full[b < kNumBlkBars ? b : kNumBlkBars - 1], par);
+                const long long k1 = clk();
                 e_w += k1 - k0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 uint32_t re[16], rx[16];
                 tmem_ld16(tmem_base + lane_base + kColE + 16 * b, re);
                 tmem_ld16(tmem_base + lane_base + kColX + 16 * b, rx);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (b == kTcBlocks - 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty);
-                }
-                // state at the start of the block -> mailbox (float)
-                tmem_st2(tmem_base + lane_base + kColMbox + 2 * b, __float_as_uint(d2f_bits(s1)), __float_as_uint(d2f_bits(s2)));
                 float p0 = 0.f, p1 = 0.f;
                 unsigned char *dst = stp + b * kChunkBytes;
                 if (first && b == 0) ep_block<true>(re, rx, dst, p, yh, p0, p1, vmax);
@@ -554,26 +568,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a2_ready[b]);
-                // block step in double: s' = A^16 s + Z_b
-                const double z0 = f2d_bits(p0), z1 = f2d_bits(p1);
-                const double n1 = fma(p.A16[0], s1, fma(p.A16[1], s2, z0));
-                const double n2 = fma(p.A16[2], s1, fma(p.A16[3], s2, z1));
-                s1 = n1;
-                s2 = n2;
-                if (b == kTcBlocks - 2) {
-                    // rows 0..159 done: the aggregate of the tile for the look-back of the tiles behind it
-                    s10_1 = s1;
-                    s10_2 = s2;
-                    if (chained) {
-                        p.lb_agg[slot * 64 + lane * 2] = s1;
-                        p.lb_agg[slot * 64 + lane * 2 + 1] = s2;
-                        __syncwarp();
-                        if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
-                    }
-                }
+                // Z_b goes to role A through the first two E columns of the block itself: they are dead until the next tile's MMA1
+                tmem_st2(tmem_base + lane_base + kColE + 16 * b, __float_as_uint(p0), __float_as_uint(p1));
                 e_m += clk() - k1;
             }
             const long long k4 = clk();
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            if (roleB) {
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&zx_ready[e]);
+                    mbar_arrive(tmem_empty);  // this warp is done with D1 (role A still reads the Z columns: it arrives after that)
+                }
+                e_l += clk() - k4;
+                continue;
+            }
+            // ---- role A: block-state recursion in double, s(b+1) = A^16 s(b) + Z_b from a zero state; the mailbox entries
+            //      Z_b are replaced by the state at the START of block b (float) for the output warp
+            mbar_wait(&zx_ready[e], par);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            double s10_1 = 0.0, s10_2 = 0.0;  // zero-state state after row 159
+            {
+                uint32_t z[kTcBlocks][2];
+#pragma unroll
+                for (int b = 0; b < kTcBlocks; b++) tmem_ld2(tmem_base + lane_base + kColE + 16 * b, z[b][0], z[b][1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);  // D1 may be overwritten
+                if (it > 0) mbar_wait(&mbox_free[e], par ^ 1);  // the output warp has read the previous tile's block states
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int b = 0; b < kTcBlocks; b++) {
+                    tmem_st2(tmem_base + lane_base + kColMbox + 2 * b, __float_as_uint(d2f_bits(s1)), __float_as_uint(d2f_bits(s2)));
+                    const double n1 = fma(p.A16[0], s1, fma(p.A16[1], s2, f2d_bits(__uint_as_float(z[b][0]))));
+                    const double n2 = fma(p.A16[2], s1, fma(p.A16[3], s2, f2d_bits(__uint_as_float(z[b][1]))));
+                    s1 = n1;
+                    s2 = n2;
+                    if (b == kTcBlocks - 2) {
+                        s10_1 = s1;
+                        s10_2 = s2;
+                    }
+                }
+            }
+            if (chained) {
+                // the aggregate of the tile for the look-back of the tiles behind it
+                p.lb_agg[slot * 64 + lane * 2] = s10_1;
+                p.lb_agg[slot * 64 + lane * 2 + 1] = s10_2;
+                __syncwarp();
+                if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
@@ -671,7 +716,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             pr[kProfEpWork] = e_m;
             pr[kProfEpLookback] = e_l;
         }
-    } else if (warp < 18) {
+    } else if (warp < 22) {
         // ================================ output warps ================================
         const int e = warp & 3;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
@@ -723,34 +768,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     sb[2 * k] = valid ? v0 : 0.f;
                     sb[2 * k + 1] = valid ? v1 : 0.f;
                 }
-                const int rc0 = (first && s == 0) ? kTcOut : kRsN * s;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t re[16], rx[16];
-                    tmem_ld16(tmem_base + lane_base + kColD2 + 64 * b + 16 * h, re);
-                    tmem_ld16(tmem_base + lane_base + kColD2 + 64 * b + 32 + 16 * h, rx);
+                const unsigned char *rcb = stage + (((first && s == 0) ? kTcRcFirst : kRsN * s) >> 3) * kKbStride;
+                float *op = outp + (size_t)(kRsN * s) * p.C;
+                // compact loop (4 outputs per trip): the kernel's hot code has to stay inside the instruction cache
+                const int ng = (s == kRsSlices - 1) ? (kTcOut - kRsN * (kRsSlices - 1) + 3) / 4 : kRsN / 4;
+#pragma unroll 1
+                for (int g = 0; g < ng; g++) {
+                    uint32_t e4[4], x4[4];
+                    tmem_ld4(tmem_base + lane_base + kColD2 + 64 * b + 4 * g, e4);
+                    tmem_ld4(tmem_base + lane_base + kColD2 + 64 * b + 32 + 4 * g, x4);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (h == 1) {
-                        asm volatile("tcgen05.fence::before_thread_sync;");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&d2_empty[b]);
-                    }
+                    const unsigned char *rcg = rcb + (g >> 1) * kKbStride + (g & 1) * 8 * kMbStride + 128;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int mi = 16 * h + i, m = kRsN * s + mi;
-                        if (m < kTcOut) {
-                            float corr = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 8; q++) corr = fmaf(p.rc[rc0 + mi][q], sb[q], corr);
-                            const float o = fmaf(__uint_as_float(re[i]) + __uint_as_float(rx[i]), p.descale_rs, corr);
-                            outp[(size_t)m * p.C] = o;
+                    for (int i = 0; i < 4; i++) {
+                        const float4 ca = *reinterpret_cast<const float4 *>(rcg + (2 * i) * kMbStride);
+                        const float4 cb = *reinterpret_cast<const float4 *>(rcg + (2 * i + 1) * kMbStride);
+                        const float c0 = fmaf(ca.y, sb[1], ca.x * sb[0]), c1 = fmaf(ca.w, sb[3], ca.z * sb[2]);
+                        const float c2 = fmaf(cb.y, sb[5], cb.x * sb[4]), c3 = fmaf(cb.w, sb[7], cb.z * sb[6]);
+                        const float o = fmaf(__uint_as_float(e4[i]) + __uint_as_float(x4[i]), p.descale_rs, (c0 + c1) + (c2 + c3));
+                        if (kRsN * s + 4 * g + i < kTcOut) {
+                            *op = o;
                             if (meter) {
                                 m_peak = fmaxf(m_peak, fabsf(o));
                                 m_sumsq += (double)o * (double)o;
                             }
                         }
+                        op += p.C;
                     }
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d2_empty[b]);
             }
             r_m += clk() - k5;
             if (meter) {
@@ -758,7 +806,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 atomicAdd(p.meter_sumsq + c, m_sumsq);
             }
         }
-        if (p.prof && warp == 14 && lane == 0) {
+        if (p.prof && warp == 18 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
             pr[kProfOutWait] = r_w;
             pr[kProfOutMain] = r_m;
@@ -775,15 +823,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
                 const bool first = (tile / p.n_cg) == 0;
                 int pair = 0;
+#pragma unroll 1
                 for (int s = 0; s < kRsSlices; s++, nsl++) {
                     const uint32_t b = nsl & 1u;
                     const int nch = (s == kRsSlices - 1) ? 3 : 4;
                     const long long c0 = clk();
-                    mbar_wait(&a2_ready[2 * s + nch - 1], it & 1);  // blocks are staged in order
+                    mbar_wait(&a2_ready[2 * s + nch - 1], it & 1);  // each drain role stages its blocks (even / odd) in order
+                    mbar_wait(&a2_ready[2 * s + nch - 2], it & 1);
                     w_y += clk() - c0;
                     mbar_wait(&d2_empty[b], ((nsl >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t dE = tmem_base + kColD2 + 64 * b, dX = dE + kRsN;
+#pragma unroll 1
                     for (int k = 0; k < nch; k++, pair++) {
                         const uint32_t a_base = st0 + (2 * s + k) * kChunkBytes;
                         const uint64_t a0 = make_desc(a_base, kKbStride, kMbStride), a1 = make_desc(a_base + kPieceBytes, kKbStride, kMbStride);
