@@ -235,12 +235,13 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     s.tc_sh = fixed_shift(h.data(), kTcMaxTaps);
     const double sh = std::ldexp(1.0, s.tc_sh);
     std::vector<__half> tab((size_t)TcTables::kHalfs);
-    __half *T0 = tab.data(), *T1 = T0 + TcTables::kT, *T2 = T1 + TcTables::kT;
+    __half *T0 = tab.data(), *T1 = T0 + TcTables::kT, *T2 = T1 + TcTables::kT, *T3 = T2 + TcTables::kT;
     for (int e = -21; e <= 53; e++)
         for (int n_i = 0; n_i < 8; n_i++)
             for (int k_i = 0; k_i < 8; k_i++) {
                 const size_t idx = (size_t)(e + 21) * 64 + n_i * 8 + k_i;
                 split_fixed3(gtap(8 * e + n_i - k_i + 1) * sh, T0[idx], T1[idx], T2[idx]);
+                T3[idx] = __float2half_rn((float)(gtap(8 * e + n_i - k_i + 1) * sh));
             }
     PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
     // MMA2: P = blockdiag(G16) * R.  R[row][m] = coef[branch(m)][i_m - row] is the polyphase matrix of one tile (row = frame + 15;
@@ -486,6 +487,13 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
                                       "out_wait", "out_main", "mma2_wait_a2"};
         const double tiles_per_cta = (double)total / grid;
         fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
+        fprintf(stderr, "  mma_issue per chunk:");
+        for (int q = 0; q < kTcChunks; q++) {
+            double sum = 0;
+            for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + tc::kProfChunk0 + q];
+            fprintf(stderr, " %.0f", sum / grid / tiles_per_cta);
+        }
+        fprintf(stderr, "\n");
         for (int k = 0; k <= tc::kProfMma2Wait; k++) {
             double sum = 0;
             for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + k];

@@ -66,7 +66,8 @@ constexpr int kTcLead = 272;        // frames of the window before the tile star
 constexpr int kTcMaxTaps = 257;
 constexpr int kTcCores = 75;        // Toeplitz core matrices per piece
 constexpr int kTcThreads = 736;     // 23 warps: TMA, MMA1, 2x4 converters, 2x4 drain, 4 output, MMA2
-constexpr int kRawStages = 4, kCvtStages = 3;
+constexpr int kRawStages = 6, kCvtStages = 3;
+constexpr int kTcRing = 8;          // chunks of the MMA2 A operand kept in shared memory (block b lives in slot b % 8)
 constexpr int kTcBlocks = kTcN / 16;     // 11 blocks of 16 rows: biquad blocks == K chunks of MMA2
 constexpr int kTcFirstDone = 17;    // column block b of D1 is complete after chunk b + 17 (the last two after chunk 26)
 constexpr int kRsSlices = 5;        // slices of 32 outputs; slice s reads row blocks [2s, 2s+4) (the last one 3)
@@ -74,8 +75,8 @@ constexpr int kRsN = 32;
 constexpr int kRsPairs = 19;        // (slice, block) blocks of P; entry 19 is (0, 0) for tile 0 (rows 0..14 are y history)
 
 struct TcTables {  // tables in global memory, copied to shared at kernel start
-    static constexpr int kT = kTcCores * 64;           // T0 T1 T2: 75*64 halfs each
-    static constexpr int kHalfs = 3 * kT;
+    static constexpr int kT = kTcCores * 64;           // T0 T1 T2 (three-piece split) and T3 (the tap rounded once): 75*64 halfs each
+    static constexpr int kHalfs = 4 * kT;
     static constexpr int kB2 = (kRsPairs + 1) * 2 * 512;  // then P blocks [pair][piece][nb 4][kb 2][8][8] halfs
     static constexpr int kBytes = (kHalfs + kB2) * 2;
 };
@@ -191,6 +192,16 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a converged warp.  The tcgen05 / TMA instructions take their operands from uniform registers: issued under
+// `if (lane == 0)` (divergent code) every one of them is wrapped in an ELECT / BRA.U.ANY waterfall with R2UR moves, which cost
+// the single issuing thread ~100 cycles per MMA (measured).  With the whole warp running the control flow and only the issue
+// elected, the descriptors stay in uniform registers.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 {
     asm volatile(
@@ -236,7 +247,7 @@ __device__ __forceinline__ float d2f_bits(double d)  // round to nearest (ties u
 
 __device__ __forceinline__ long long clk() { return clock64(); }
 enum { kProfProdWait = 0, kProfMmaWaitTmem, kProfMmaWaitCvt, kProfMmaIssue, kProfCvtWaitRaw, kProfCvtWaitCvt, kProfCvtWork,
-       kProfEpWaitBlk, kProfEpWork, kProfEpLookback, kProfTotal, kProfOutWait, kProfOutMain, kProfMma2Wait, kProfCount = 16 };
+       kProfEpWaitBlk, kProfEpWork, kProfEpLookback, kProfTotal, kProfOutWait, kProfOutMain, kProfMma2Wait, kProfChunk0 = 16, kProfCount = 48 };
 
 // shared memory map (bytes)
 constexpr int kRawStageBytes = 16 * kTcCh * 4;                  // 8 KB: 4 sub-tiles of 16 rows x 128 B
@@ -244,16 +255,17 @@ constexpr int kCvtStageBytes = 2 * 16 * kTcCh * 2;              // 8 KB: x0 then
 constexpr int kOffRaw = 0;
 constexpr int kOffCvt = kOffRaw + kRawStages * kRawStageBytes;
 constexpr int kOffTab = kOffCvt + kCvtStages * kCvtStageBytes;
-constexpr int kTabBytes = TcTables::kBytes;                     // 28800 + 40960
+constexpr int kTabBytes = TcTables::kBytes;                     // 38400 + 40960
 // A operand of MMA2: 11 chunks of 16 rows; a chunk is [piece 2][kb 2][mb 16] core matrices of 8 rows x 16 B at a
 // 144 B stride (instead of 128 B: the 2-byte scatter stores of a warp then hit 16 different words)
 constexpr int kMbStride = 144, kKbStride = 16 * kMbStride, kPieceBytes = 2 * kKbStride, kChunkBytes = 2 * kPieceBytes;
 constexpr int kOffStage = ((kOffTab + kTabBytes + 127) / 128) * 128;
-constexpr int kStageBytes = kTcBlocks * kChunkBytes;            // 101376
+constexpr int kStageBytes = kTcRing * kChunkBytes;              // 73728
 constexpr int kOffSstate = kOffStage + kStageBytes;             // [4][2][32] float: incoming state of the tile
-constexpr int kOffBar = kOffSstate + 4 * 2 * 32 * 4;
+constexpr int kOffQtab = kOffSstate + 4 * 2 * 32 * 4;          // [27] uint4: per-chunk MMA1 constants (the issuing thread is latency-bound)
+constexpr int kOffBar = kOffQtab + 32 * 16;
 constexpr int kNumBlkBars = kTcChunks - kTcFirstDone;           // 10: one per chunk 17..26
-constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + 1 + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 4;
+constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + 1 + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 4 + 2;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
@@ -262,6 +274,7 @@ static_assert(kOffStage % 16 == 0 && kChunkBytes % 16 == 0, "UMMA descriptor ali
 // byte offset (from the staging tile) of half h (4 floats) of row m of the rc table: pad 2m+h of the 704 pads
 __host__ __device__ constexpr int rc_pad_off(int m, int h) { return (m >> 3) * kKbStride + (2 * (m & 7) + h) * kMbStride + 128; }
 static_assert(rc_pad_off(kTcRcRows - 1, 1) + 16 <= kStageBytes, "rc table fits in the pads");
+static_assert(kTcBlocks - kTcRing == 3, "blocks 8, 9 reuse the slots of blocks 0, 1 (read by slice 0 only), block 10 that of block 2 (slices 0, 1)");
 
 // TMEM columns: D1 = E [0,176) + X [176,352); D2 double-buffered slices [E2 | X2] of 32 + 32 columns from 352;
 // mailbox of the 11 block states (2 columns each, 24 with padding) from 480
@@ -315,7 +328,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     uint64_t *state_ready = d2_empty + 2;           // [4]  drain warp e -> output warp e: incoming state in sstate
     uint64_t *mbox_ready = state_ready + 4;         // [4]  drain warp e -> output warp e: block states in the TMEM mailbox
     uint64_t *mbox_free = mbox_ready + 4;           // [4]  output warp e -> drain warps e
-    uint64_t *zx_ready = mbox_free + 4;             // [4]  drain warp B -> drain warp A: the Z of the odd blocks are in the mailbox
+    uint64_t *zx_ready = mbox_free + 4;             // [4]  drain warp B -> drain warp A: the Z of the odd blocks are in D1's dead columns
+    uint64_t *slice_done = zx_ready + 4;            // [2]  MMA2 (commit) -> drain: slices 0 / 1 have read ring slots 0,1 / 2
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmemSlot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -348,6 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&mbox_ready[i], 1);
             mbar_init(&mbox_free[i], 1);
             mbar_init(&zx_ready[i], 1);
+            if (i < 2) mbar_init(&slice_done[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -396,8 +411,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ================================ MMA1 issuer =================================
-        if (lane == 0) {
-            const uint32_t t0 = smem_u32(tab), t1 = t0 + TcTables::kT * 2, t2 = t1 + TcTables::kT * 2;
+        // Only the band of the Toeplitz matrix is multiplied: chunk q (frames f0-272+16q ..+15) reaches output columns
+        // [16q-257, 16q+14], i.e. 8-column blocks [2q-33, 2q+1] clipped to [0, 21] and widened to an even count (N % 16 == 0).
+        // Chunk 0 runs at full width with accumulate = 0: it zeroes the accumulators.  One thread issues everything, so its
+        // own instruction latency matters: the per-chunk constants are tabulated once (x: B descriptor offset >> 4,
+        // y: instruction descriptor, z: first accumulator column).
+        uint4 *qtab = reinterpret_cast<uint4 *>(smem + kOffQtab);
+        if (lane < kTcChunks) {
+            const int q = lane;
+            int nb0 = 0, nbl = kTcN / 8;
+            if (q > 0) {
+                int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
+                if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
+                nb0 = lo;
+                nbl = hi - lo + 1;
+            }
+            qtab[q] = make_uint4((uint32_t)((52 - 2 * q + nb0) * 128) >> 4, make_idesc(8 * nbl), (uint32_t)(8 * nb0), 0u);
+        }
+        __syncwarp();
+        {
+            const uint32_t t0 = smem_u32(tab);
+            const uint64_t bd0 = make_desc(t0, 128, 128), bd1 = make_desc(t0 + TcTables::kT * 2, 128, 128);
+            const uint64_t bd2 = make_desc(t0 + TcTables::kT * 4, 128, 128), bd3 = make_desc(t0 + TcTables::kT * 6, 128, 128);
+            const uint64_t ad0 = make_desc(smem_u32(cvt), 2048, 128);  // stage s: + s * kCvtStageBytes >> 4; x1: + 4096 >> 4
             int s = 0, ph = 0, tph = 0;
             long long w_t = 0, w_c = 0, w_i = 0;
             const long long kstart = clk();
@@ -408,43 +444,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll 1
                 for (int q = 0; q < kTcChunks; q++) {
+                    const uint4 qc = qtab[q];
+                    const uint64_t a0 = ad0 + (uint64_t)(s * (kCvtStageBytes >> 4)), a1 = a0 + (4096 >> 4);
+                    const uint64_t b0 = bd0 + qc.x, b1 = bd1 + qc.x, b2 = bd2 + qc.x, b3 = bd3 + qc.x;
+                    const uint32_t dE = tmem_base + kColE + qc.z, dX = tmem_base + kColX + qc.z;
                     c0 = clk();
                     mbar_wait(&cvt_full[s], ph);
                     const long long c1 = clk();
                     w_c += c1 - c0;
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t a_base = smem_u32(cvt + s * kCvtStageBytes);
-                    const uint64_t a0 = make_desc(a_base, 2048, 128), a1 = make_desc(a_base + 4096, 2048, 128);
-                    // Only the band of the Toeplitz matrix is multiplied: chunk q (frames f0-272+16q ..+15) reaches output
-                    // columns [16q-257, 16q+14], i.e. 8-column blocks [2q-33, 2q+1] clipped to [0, 21] and widened to an even
-                    // count (N % 16 == 0).  Chunk 0 runs at full width with accumulate = 0: it zeroes the accumulators.
-                    int nb0 = 0, nbl = kTcN / 8;
-                    if (q > 0) {
-                        int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
-                        if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
-                        nb0 = lo;
-                        nbl = hi - lo + 1;
+                    if (elect_one()) {
+                        if (!(p.dbg & 1)) {
+                            umma(dE, a0, b0, qc.y, q > 0);   // x0 h0: exact, integers < 2^24
+                            umma(dX, a0, b1, qc.y, q > 0);   // x0 (h1 + h2): the tap's remainder in two pieces
+                            umma(dX, a0, b2, qc.y, 1);
+                            umma(dX, a1, b3, qc.y, 1);       // x1 h: |x1| <= 1/2, the tap rounded once (2^-12 relative) is enough
+                        }
+                        umma_commit(&cvt_empty[s]);  // frees the A stage when these MMAs have read it
+                        if (q >= kTcFirstDone) umma_commit(&blk_full[q - kTcFirstDone]);  // column block q-17 (after 26: 9 and 10) is final
                     }
-                    const uint32_t toff = (52 - 2 * q + nb0) * 128;
-                    const uint64_t b0 = make_desc(t0 + toff, 128, 128), b1 = make_desc(t1 + toff, 128, 128);
-                    const uint64_t b2 = make_desc(t2 + toff, 128, 128);
-                    const uint32_t acc = q > 0, idesc = make_idesc(8 * nbl);
-                    const uint32_t dE = tmem_base + kColE + 8 * nb0, dX = tmem_base + kColX + 8 * nb0;
-                    if (!(p.dbg & 1)) {
-                        umma(dE, a0, b0, idesc, acc);   // exact: integers < 2^24
-                        umma(dX, a0, b1, idesc, acc);
-                        umma(dX, a0, b2, idesc, 1);
-                        umma(dX, a1, b0, idesc, 1);
-                        umma(dX, a1, b1, idesc, 1);
-                    }
-                    umma_commit(&cvt_empty[s]);  // frees the A stage when these MMAs have read it
-                    if (q >= kTcFirstDone) umma_commit(&blk_full[q - kTcFirstDone]);  // column block q-17 (after 26: 9 and 10) is final
-                    w_i += clk() - c1;
+                    __syncwarp();
+                    const long long c2 = clk();
+                    w_i += c2 - c1;
+                    if (p.prof && lane == 0) p.prof[blockIdx.x * kProfCount + kProfChunk0 + q] += c2 - c1;
                     if (++s == kCvtStages) { s = 0; ph ^= 1; }
                 }
                 tph ^= 1;
             }
-            if (p.prof) {
+            if (p.prof && lane == 0) {
                 long long *pr = p.prof + blockIdx.x * kProfCount;
                 pr[kProfMmaWaitTmem] = w_t;
                 pr[kProfMmaWaitCvt] = w_c;
@@ -512,7 +539,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     *reinterpret_cast<float4 *>(hp + 4) = make_float4(v[4] * is, v[5] * is, v[6] * is, v[7] * is);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+            if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&cvt_full[cs]);
@@ -562,10 +589,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 tmem_ld16(tmem_base + lane_base + kColX + 16 * b, rx);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float p0 = 0.f, p1 = 0.f;
-                unsigned char *dst = stp + b * kChunkBytes;
+                unsigned char *dst = stp + (b % kTcRing) * kChunkBytes;
+                if (b >= kTcRing) mbar_wait(&slice_done[b == kTcBlocks - 1 ? 1 : 0], par);  // the slot's previous block has been multiplied
                 if (first && b == 0) ep_block<true>(re, rx, dst, p, yh, p0, p1, vmax);
                 else ep_block<false>(re, rx, dst, p, yh, p0, p1, vmax);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+                if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a2_ready[b]);
                 // Z_b goes to role A through the first two E columns of the block itself: they are dead until the next tile's MMA1
@@ -695,7 +723,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 // recursion runs row by row, from the pieces of f just written (f * 2^10 = f0 + f1)
                 const double nb1 = p.b1, nb2 = p.b2, na1 = -p.a1, na2 = -p.a2;
                 for (int r = 0; r < kTcHr; r++) {
-                    const unsigned char *d = stp + (kTcBlocks - 1) * kChunkBytes + (r >> 3) * kKbStride + (r & 7) * 16;
+                    const unsigned char *d = stp + ((kTcBlocks - 1) % kTcRing) * kChunkBytes + (r >> 3) * kKbStride + (r & 7) * 16;
                     const double x = (double)((__half2float(*reinterpret_cast<const __half *>(d)) +
                                                __half2float(*reinterpret_cast<const __half *>(d + kPieceBytes))) * p.inv_fgrid);
                     const double v = fma(p.b0, x, I0);
@@ -813,7 +841,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         }
     } else {
         // ================================ MMA2 issuer =================================
-        if (lane == 0) {
+        {
             const uint32_t st0 = smem_u32(stage);
             const uint32_t b2 = smem_u32(tab) + TcTables::kHalfs * 2;
             constexpr uint32_t idesc32 = make_idesc(kRsN), idesc64 = make_idesc(2 * kRsN);
@@ -836,21 +864,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     const uint32_t dE = tmem_base + kColD2 + 64 * b, dX = dE + kRsN;
 #pragma unroll 1
                     for (int k = 0; k < nch; k++, pair++) {
-                        const uint32_t a_base = st0 + (2 * s + k) * kChunkBytes;
+                        const uint32_t a_base = st0 + ((2 * s + k) % kTcRing) * kChunkBytes;
                         const uint64_t a0 = make_desc(a_base, kKbStride, kMbStride), a1 = make_desc(a_base + kPieceBytes, kKbStride, kMbStride);
                         const uint32_t tb = b2 + ((first && pair == 0) ? kRsPairs : pair) * 2048;
                         const uint64_t r0 = make_desc(tb, 128, 256), r1 = make_desc(tb + 1024, 128, 256);
-                        if (!(p.dbg & 2)) {
+                        if (!(p.dbg & 2) && elect_one()) {
                             umma(dE, a0, r0, idesc64, k > 0);  // f0 * [p0 | p1] -> [E2 | X2]; E2 exact: integers < 2^24
                             umma(dX, a1, r0, idesc32, 1);
                             umma(dX, a1, r1, idesc32, 1);
                         }
+                        __syncwarp();
                     }
-                    umma_commit(&d2_full[b]);
+                    if (elect_one()) {
+                        umma_commit(&d2_full[b]);
+                        if (s < 2) umma_commit(&slice_done[s]);
+                        if (s == kRsSlices - 1) umma_commit(stage_free);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(stage_free);
             }
-            if (p.prof) p.prof[blockIdx.x * kProfCount + kProfMma2Wait] = w_y;
+            if (p.prof && lane == 0) p.prof[blockIdx.x * kProfCount + kProfMma2Wait] = w_y;
         }
     }
 

@@ -25,21 +25,21 @@ DEVI void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, 
 {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-struct Cfg { int n, col, a_kb, a_mb, b_lbo, b_sbo, alt, dp; };
+struct Cfg { int n, col, a_kb, a_mb, b_lbo, b_sbo, alt, dp, batch4; };
 
 __global__ void __launch_bounds__(160) k(Cfg c, int reps, long long *cyc, double *sink)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 65536);
-    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + 65536 + 16);
-    volatile int *stop = reinterpret_cast<volatile int *>(smem + 65536 + 32);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + 65536 + 32);
+    volatile int *stop = reinterpret_cast<volatile int *>(smem + 65536 + 48);
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;  // halves 1.0
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid == 0) { mbar_init(bar, 1); *stop = 0; asm volatile("fence.mbarrier_init.release.cluster;"); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); *stop = 0; asm volatile("fence.mbarrier_init.release.cluster;"); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -51,7 +51,23 @@ __global__ void __launch_bounds__(160) k(Cfg c, int reps, long long *cyc, double
         const uint32_t id = make_idesc(c.n);
         long long t0 = clock64();
         for (int r = 0; r < reps; r++) {
-            if (c.n > 0) {
+            if (c.batch4) {
+                // the kernel's pattern: per chunk 4 MMAs (E, X, X, X) and a commit nobody waits for; 4 chunks per rep
+#pragma unroll 1
+                for (int u = 0; u < 4; u++) {
+                    const uint64_t as = a + (uint64_t)((u % 3) * (8192 >> 4));
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    umma(tb + c.col, as, b, id, 1);
+                    umma(tb + c.col + 176, as, b + 600, id, 1);
+                    umma(tb + c.col + 176, as, b + 1200, id, 1);
+                    umma(tb + c.col + 176, as + 256, b + 1800, id, 1);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + 1)) : "memory");
+                }
+                if ((r & 7) == 7) {
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+                    mbar_wait(bar, (r >> 3) & 1);
+                }
+            } else if (c.n > 0) {
 #pragma unroll
                 for (int u = 0; u < 16; u++) umma(tb + c.col + ((c.alt && (u & 1)) ? 192 : 0), a, b, id, 1);
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -104,6 +120,7 @@ int main()
         {0, 0, 2048, 128, 128, 128, 0, 1},    // DFMA warps alone
         {176, 0, 2048, 128, 128, 128, 1, 1},  // DFMA warps next to a saturated UMMA stream
         {32, 368, 2304, 144, 128, 256, 0, 1},
+        {176, 0, 2048, 128, 128, 128, 0, 0, 1}, {96, 8, 2048, 128, 128, 128, 0, 0, 1}, {32, 16, 2048, 128, 128, 128, 0, 0, 1}, {16, 0, 2048, 128, 128, 128, 0, 0, 1},
     };
     for (auto &cf : cfgs) {
         h[0] = h[1] = h[2] = 0;
@@ -113,6 +130,7 @@ int main()
         cudaMemcpy(h, c, 24, cudaMemcpyDeviceToHost);
         printf("N %3d col %3d A(kb %4d mb %3d) B(lbo %3d sbo %3d) alt %d : %.1f cycles/MMA (floor %.0f)", cf.n, cf.col, cf.a_kb, cf.a_mb, cf.b_lbo,
                cf.b_sbo, cf.alt, cf.n ? (double)h[0] / reps / 16 : 0.0, cf.n / 2.0);
+        if (cf.batch4) printf(" [batches of 4 + commit]");
         if (cf.dp) printf("  | DFMA: %.2f cycles/op/warp (4 warps)", h[2] ? (double)h[1] / h[2] : 0.0);
         printf("  %s\n", e == cudaSuccess ? "" : cudaGetErrorString(e));
     }
