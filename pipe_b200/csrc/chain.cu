@@ -415,7 +415,8 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
 {
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         attr_set = true;
     }
     TcParams p{};
@@ -475,7 +476,8 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         PB_CUDA(cudaMemset(d_prof, 0, sizeof(long long) * tc::kProfCount * grid));
         p.prof = d_prof;
     }
-    chain_tc_kernel<<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+    if (prof_on) chain_tc_kernel<true><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+    else chain_tc_kernel<false><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
     PB_CUDA(cudaGetLastError());
     if (prof_on) {
         PB_CUDA(cudaStreamSynchronize(stream));
@@ -487,7 +489,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
                                       "out_wait", "out_main", "mma2_wait_a2"};
         const double tiles_per_cta = (double)total / grid;
         fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
-        fprintf(stderr, "  mma_issue per chunk:");
+        fprintf(stderr, "  out: group_sync, mailbox+states, tmem ld, outputs (then unused):");
         for (int q = 0; q < kTcChunks; q++) {
             double sum = 0;
             for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + tc::kProfChunk0 + q];

@@ -65,7 +65,7 @@ constexpr int kTcWin = kTcChunks * 16;
 constexpr int kTcLead = 272;        // frames of the window before the tile start
 constexpr int kTcMaxTaps = 257;
 constexpr int kTcCores = 75;        // Toeplitz core matrices per piece
-constexpr int kTcThreads = 736;     // 23 warps: TMA, MMA1, 2x4 converters, 2x4 drain, 4 output, MMA2
+constexpr int kTcThreads = 864;     // 27 warps: TMA, MMA1, 2x4 converters, 2x4 drain, 2x4 output, MMA2
 constexpr int kRawStages = 6, kCvtStages = 3;
 constexpr int kTcRing = 8;          // chunks of the MMA2 A operand kept in shared memory (block b lives in slot b % 8)
 constexpr int kTcBlocks = kTcN / 16;     // 11 blocks of 16 rows: biquad blocks == K chunks of MMA2
@@ -192,6 +192,9 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Named barrier over the 4 warps of a role group.  Only the group's first warp sleeps on an mbarrier; the others wait here,
+// which costs no issue slots (every mbarrier arrival wakes the warps parked on the CTA's mbarriers).
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 // One lane of a converged warp.  The tcgen05 / TMA instructions take their operands from uniform registers: issued under
 // `if (lane == 0)` (divergent code) every one of them is wrapped in an ELECT / BRA.U.ANY waterfall with R2UR moves, which cost
 // the single issuing thread ~100 cycles per MMA (measured).  With the whole warp running the control flow and only the issue
@@ -262,8 +265,7 @@ constexpr int kMbStride = 144, kKbStride = 16 * kMbStride, kPieceBytes = 2 * kKb
 constexpr int kOffStage = ((kOffTab + kTabBytes + 127) / 128) * 128;
 constexpr int kStageBytes = kTcRing * kChunkBytes;              // 73728
 constexpr int kOffSstate = kOffStage + kStageBytes;             // [4][2][32] float: incoming state of the tile
-constexpr int kOffQtab = kOffSstate + 4 * 2 * 32 * 4;          // [27] uint4: per-chunk MMA1 constants (the issuing thread is latency-bound)
-constexpr int kOffBar = kOffQtab + 32 * 16;
+constexpr int kOffBar = kOffSstate + 4 * 2 * 32 * 4;
 constexpr int kNumBlkBars = kTcChunks - kTcFirstDone;           // 10: one per chunk 17..26
 constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + 1 + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 4 + 2;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
@@ -307,6 +309,8 @@ __device__ __forceinline__ void ep_block(const uint32_t (&re)[16], const uint32_
     }
 }
 
+// PROF: per-role cycle counters (PB_TC_PROF=1); a compile-time switch, the counters cost the single-warp issue loops dearly
+template <bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_constant__ TcParams p)
 {
     using namespace tc;
@@ -315,7 +319,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     unsigned char *cvt = smem + kOffCvt;
     __half *tab = reinterpret_cast<__half *>(smem + kOffTab);
     unsigned char *stage = smem + kOffStage;
-    float *sstate = reinterpret_cast<float *>(smem + kOffSstate);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
     uint64_t *raw_full = bars, *raw_empty = bars + kRawStages;
     uint64_t *cvt_full = bars + 2 * kRawStages, *cvt_empty = cvt_full + kCvtStages;
@@ -343,24 +346,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     if (tid == 32) {
         for (int i = 0; i < kRawStages; i++) {
             mbar_init(&raw_full[i], 1);
-            mbar_init(&raw_empty[i], 4);
+            mbar_init(&raw_empty[i], 1);
         }
         for (int i = 0; i < kCvtStages; i++) {
-            mbar_init(&cvt_full[i], 4);
+            mbar_init(&cvt_full[i], 1);
             mbar_init(&cvt_empty[i], 1);
         }
         for (int i = 0; i < kNumBlkBars; i++) mbar_init(&blk_full[i], 1);
         mbar_init(tmem_empty, 8);
-        for (int i = 0; i < kTcBlocks; i++) mbar_init(&a2_ready[i], 4);
+        for (int i = 0; i < kTcBlocks; i++) mbar_init(&a2_ready[i], 1);
         mbar_init(stage_free, 1);
         for (int i = 0; i < 2; i++) {
             mbar_init(&d2_full[i], 1);
-            mbar_init(&d2_empty[i], 4);
+            mbar_init(&d2_empty[i], 1);
         }
         for (int i = 0; i < 4; i++) {
             mbar_init(&state_ready[i], 1);
             mbar_init(&mbox_ready[i], 1);
-            mbar_init(&mbox_free[i], 1);
+            mbar_init(&mbox_free[i], 2);
             mbar_init(&zx_ready[i], 1);
             if (i < 2) mbar_init(&slice_done[i], 1);
         }
@@ -388,9 +391,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
                 const int f0 = t * kTcFrames, ch0 = cg * kTcCh;
                 for (int q = 0; q < kTcChunks; q++) {
-                    const long long c0 = clk();
+                    const long long c0 = (PROF ? clk() : 0ll);
                     mbar_wait(&raw_empty[s], ph ^ 1);
-                    pw += clk() - c0;
+                    pw += (PROF ? clk() : 0ll) - c0;
                     if (p.dbg & 16) {  // development: no loads
                         mbar_arrive(&raw_full[s]);
                         if (++s == kRawStages) { s = 0; ph ^= 1; }
@@ -407,28 +410,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     if (++s == kRawStages) { s = 0; ph ^= 1; }
                 }
             }
-            if (p.prof) p.prof[blockIdx.x * kProfCount + kProfProdWait] = pw;
+            if (PROF && p.prof) p.prof[blockIdx.x * kProfCount + kProfProdWait] = pw;
         }
     } else if (warp == 1) {
         // ================================ MMA1 issuer =================================
         // Only the band of the Toeplitz matrix is multiplied: chunk q (frames f0-272+16q ..+15) reaches output columns
         // [16q-257, 16q+14], i.e. 8-column blocks [2q-33, 2q+1] clipped to [0, 21] and widened to an even count (N % 16 == 0).
-        // Chunk 0 runs at full width with accumulate = 0: it zeroes the accumulators.  One thread issues everything, so its
-        // own instruction latency matters: the per-chunk constants are tabulated once (x: B descriptor offset >> 4,
-        // y: instruction descriptor, z: first accumulator column).
-        uint4 *qtab = reinterpret_cast<uint4 *>(smem + kOffQtab);
-        if (lane < kTcChunks) {
-            const int q = lane;
-            int nb0 = 0, nbl = kTcN / 8;
-            if (q > 0) {
-                int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
-                if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
-                nb0 = lo;
-                nbl = hi - lo + 1;
-            }
-            qtab[q] = make_uint4((uint32_t)((52 - 2 * q + nb0) * 128) >> 4, make_idesc(8 * nbl), (uint32_t)(8 * nb0), 0u);
-        }
-        __syncwarp();
+        // Chunk 0 runs at full width with accumulate = 0: it zeroes the accumulators.  The warp runs the loop converged and elects
+        // one lane per issue (x: B descriptor offset >> 4, y: instruction descriptor, z: first accumulator column).
         {
             const uint32_t t0 = smem_u32(tab);
             const uint64_t bd0 = make_desc(t0, 128, 128), bd1 = make_desc(t0 + TcTables::kT * 2, 128, 128);
@@ -436,21 +425,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const uint64_t ad0 = make_desc(smem_u32(cvt), 2048, 128);  // stage s: + s * kCvtStageBytes >> 4; x1: + 4096 >> 4
             int s = 0, ph = 0, tph = 0;
             long long w_t = 0, w_c = 0, w_i = 0;
-            const long long kstart = clk();
+            const long long kstart = (PROF ? clk() : 0ll);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                long long c0 = clk();
+                long long c0 = (PROF ? clk() : 0ll);
                 mbar_wait(tmem_empty, tph ^ 1);  // the previous tile's D1 has been read
-                w_t += clk() - c0;
+                w_t += (PROF ? clk() : 0ll) - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll 1
+                static_assert(kTcChunks % kCvtStages == 0, "the chunk loop is unrolled by the number of A stages");
+#pragma unroll 3
                 for (int q = 0; q < kTcChunks; q++) {
-                    const uint4 qc = qtab[q];
+                    // everything here is warp-uniform arithmetic on the loop counter
+                    int nb0 = 0, nbl = kTcN / 8;
+                    if (q > 0) {
+                        int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
+                        if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
+                        nb0 = lo;
+                        nbl = hi - lo + 1;
+                    }
+                    const uint4 qc = make_uint4((uint32_t)((52 - 2 * q + nb0) * 128) >> 4, make_idesc(8 * nbl), (uint32_t)(8 * nb0), 0u);
                     const uint64_t a0 = ad0 + (uint64_t)(s * (kCvtStageBytes >> 4)), a1 = a0 + (4096 >> 4);
                     const uint64_t b0 = bd0 + qc.x, b1 = bd1 + qc.x, b2 = bd2 + qc.x, b3 = bd3 + qc.x;
                     const uint32_t dE = tmem_base + kColE + qc.z, dX = tmem_base + kColX + qc.z;
-                    c0 = clk();
+                    c0 = (PROF ? clk() : 0ll);
                     mbar_wait(&cvt_full[s], ph);
-                    const long long c1 = clk();
+                    const long long c1 = (PROF ? clk() : 0ll);
                     w_c += c1 - c0;
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (elect_one()) {
@@ -464,19 +462,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                         if (q >= kTcFirstDone) umma_commit(&blk_full[q - kTcFirstDone]);  // column block q-17 (after 26: 9 and 10) is final
                     }
                     __syncwarp();
-                    const long long c2 = clk();
+                    const long long c2 = (PROF ? clk() : 0ll);
                     w_i += c2 - c1;
-                    if (p.prof && lane == 0) p.prof[blockIdx.x * kProfCount + kProfChunk0 + q] += c2 - c1;
                     if (++s == kCvtStages) { s = 0; ph ^= 1; }
                 }
                 tph ^= 1;
             }
-            if (p.prof && lane == 0) {
+            if (PROF && p.prof && lane == 0) {
                 long long *pr = p.prof + blockIdx.x * kProfCount;
                 pr[kProfMmaWaitTmem] = w_t;
                 pr[kProfMmaWaitCvt] = w_c;
                 pr[kProfMmaIssue] = w_i;
-                pr[kProfTotal] = clk() - kstart;
+                pr[kProfTotal] = (PROF ? clk() : 0ll) - kstart;
             }
         }
     } else if (warp < 10) {
@@ -497,11 +494,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const bool last = (t == p.n_tiles - 1);
             const int rs = g % kRawStages, rph = (g / kRawStages) & 1;
             const int cs = g % kCvtStages, cph = (g / kCvtStages) & 1;
-            const long long c0 = clk();
-            mbar_wait(&raw_full[rs], rph);
-            const long long c1 = clk();
-            mbar_wait(&cvt_empty[cs], cph ^ 1);
-            const long long c2 = clk();
+            const long long c0 = (PROF ? clk() : 0ll);
+            if (cw == 0) mbar_wait(&raw_full[rs], rph);
+            const long long c1 = (PROF ? clk() : 0ll);
+            if (cw == 0) mbar_wait(&cvt_empty[cs], cph ^ 1);
+            group_sync(1 + grp);
+            const long long c2 = (PROF ? clk() : 0ll);
             w_r += c1 - c0;
             w_c += c2 - c1;
             const bool hist = (f0 - kTcLead + 16 * q) < 0;
@@ -540,15 +538,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 }
             }
             if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
-            __syncwarp();
-            if (lane == 0) {
+            group_sync(1 + grp);
+            if (cw == 0 && lane == 0) {
                 mbar_arrive(&cvt_full[cs]);
                 mbar_arrive(&raw_empty[rs]);
             }
-            w_w += clk() - c2;
+            w_w += (PROF ? clk() : 0ll) - c2;
         }
         if (vmax > 60000.f) atomicExch(p.err_flag, 2);
-        if (p.prof && warp == 2 && lane == 0) {
+        if (PROF && p.prof && warp == 2 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
             pr[kProfCvtWaitRaw] = w_r;
             pr[kProfCvtWaitCvt] = w_c;
@@ -576,12 +574,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const size_t slot = (size_t)grp * p.n_tiles + t;
             const bool chained = !first && !last;
             const float *yh = p.yhist + c;
-            if (it > 0) mbar_wait(stage_free, par ^ 1);  // MMA2 has consumed the previous tile's pieces
+            const bool gl = (warp & 3) == 2;  // first warp of the role group (warps 10 / 14)
+            const int gid = roleB ? 4 : 3;
+            if (gl && it > 0) mbar_wait(stage_free, par ^ 1);  // MMA2 has consumed the previous tile's pieces
 #pragma unroll 1
             for (int b = roleB ? 1 : 0; b < kTcBlocks; b += 2) {
-                const long long k0 = clk();
-                mbar_wait(&blk_full[b < kNumBlkBars ? b : kNumBlkBars - 1], par);
-                const long long k1 = clk();
+                const long long k0 = (PROF ? clk() : 0ll);
+                if (gl) {
+                    mbar_wait(&blk_full[b < kNumBlkBars ? b : kNumBlkBars - 1], par);
+                    if (b >= kTcRing) mbar_wait(&slice_done[b == kTcBlocks - 1 ? 1 : 0], par);  // the slot's previous block has been multiplied
+                }
+                group_sync(gid);
+                const long long k1 = (PROF ? clk() : 0ll);
                 e_w += k1 - k0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 uint32_t re[16], rx[16];
@@ -590,17 +594,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float p0 = 0.f, p1 = 0.f;
                 unsigned char *dst = stp + (b % kTcRing) * kChunkBytes;
-                if (b >= kTcRing) mbar_wait(&slice_done[b == kTcBlocks - 1 ? 1 : 0], par);  // the slot's previous block has been multiplied
                 if (first && b == 0) ep_block<true>(re, rx, dst, p, yh, p0, p1, vmax);
                 else ep_block<false>(re, rx, dst, p, yh, p0, p1, vmax);
                 if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a2_ready[b]);
+                group_sync(gid);
+                if (gl && lane == 0) mbar_arrive(&a2_ready[b]);
                 // Z_b goes to role A through the first two E columns of the block itself: they are dead until the next tile's MMA1
                 tmem_st2(tmem_base + lane_base + kColE + 16 * b, __float_as_uint(p0), __float_as_uint(p1));
-                e_m += clk() - k1;
+                e_m += (PROF ? clk() : 0ll) - k1;
             }
-            const long long k4 = clk();
+            const long long k4 = (PROF ? clk() : 0ll);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             if (roleB) {
                 asm volatile("tcgen05.fence::before_thread_sync;");
@@ -609,7 +612,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     mbar_arrive(&zx_ready[e]);
                     mbar_arrive(tmem_empty);  // this warp is done with D1 (role A still reads the Z columns: it arrives after that)
                 }
-                e_l += clk() - k4;
+                e_l += (PROF ? clk() : 0ll) - k4;
                 continue;
             }
             // ---- role A: block-state recursion in double, s(b+1) = A^16 s(b) + Z_b from a zero state; the mailbox entries
@@ -617,6 +620,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_wait(&zx_ready[e], par);
             asm volatile("tcgen05.fence::after_thread_sync;");
             double s10_1 = 0.0, s10_2 = 0.0;  // zero-state state after row 159
+            float szs[kTcBlocks][2];          // zero-state state at the start of each block
             {
                 uint32_t z[kTcBlocks][2];
 #pragma unroll
@@ -625,11 +629,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty);  // D1 may be overwritten
-                if (it > 0) mbar_wait(&mbox_free[e], par ^ 1);  // the output warp has read the previous tile's block states
                 double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int b = 0; b < kTcBlocks; b++) {
-                    tmem_st2(tmem_base + lane_base + kColMbox + 2 * b, __float_as_uint(d2f_bits(s1)), __float_as_uint(d2f_bits(s2)));
+                    szs[b][0] = d2f_bits(s1);
+                    szs[b][1] = d2f_bits(s2);
                     const double n1 = fma(p.A16[0], s1, fma(p.A16[1], s2, f2d_bits(__uint_as_float(z[b][0]))));
                     const double n2 = fma(p.A16[2], s1, fma(p.A16[3], s2, f2d_bits(__uint_as_float(z[b][1]))));
                     s1 = n1;
@@ -647,11 +651,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&mbox_ready[e]);
-
             // ---- incoming state: decoupled look-back (same protocol and arrays as K1, 32-channel groups)
             double q1 = 0.0, q2 = 0.0;
             if (first) {
@@ -704,10 +703,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                         }
                 }
             }
-            sstate[(e * 2 + 0) * 32 + lane] = d2f_bits(q1);
-            sstate[(e * 2 + 1) * 32 + lane] = d2f_bits(q2);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&state_ready[e]);
+            // ---- true state at the start of every block = zero-state part + response to the incoming state -> output warps
+            {
+                const float qf0 = d2f_bits(q1), qf1 = d2f_bits(q2);
+                const int fi = first ? 1 : 0;
+                if (it > 0) mbar_wait(&mbox_free[e], par ^ 1);  // the output warps have read the previous tile's block states
+                asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                for (int b = 0; b < kTcBlocks; b++) {
+                    const float *M = p.Mb[fi][b];
+                    const float v0 = fmaf(M[0], qf0, fmaf(M[1], qf1, szs[b][0])), v1 = fmaf(M[2], qf0, fmaf(M[3], qf1, szs[b][1]));
+                    tmem_st2(tmem_base + lane_base + kColMbox + 2 * b, __float_as_uint(v0), __float_as_uint(v1));
+                }
+                tmem_st2(tmem_base + lane_base + kColMbox + 2 * kTcBlocks, 0u, 0u);  // the last slice reads a fourth, absent block
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&mbox_ready[e]);
+            }
             // true state after row 159
             double I0 = q1, I1 = q2;
             mat2_apply(first ? p.AL_first : p.AL, I0, I1);
@@ -735,20 +748,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 p.bq_state_next[2 * c] = I0;
                 p.bq_state_next[2 * c + 1] = I1;
             }
-            e_l += clk() - k4;
+            e_l += (PROF ? clk() : 0ll) - k4;
         }
         if (vmax > 60000.f) atomicExch(p.err_flag, 2);
-        if (p.prof && warp == 10 && lane == 0) {
+        if (PROF && p.prof && warp == 10 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
             pr[kProfEpWaitBlk] = e_w;
             pr[kProfEpWork] = e_m;
             pr[kProfEpLookback] = e_l;
         }
-    } else if (warp < 22) {
+    } else if (warp < 26) {
         // ================================ output warps ================================
+        // two warps per TMEM lane quadrant: warps 18-21 take outputs 0..15 of every slice, warps 22-25 outputs 16..31
         const int e = warp & 3;
+        const int hsel = warp >= 22 ? 1 : 0;
         const uint32_t lane_base = (uint32_t)(e * 32) << 16;
-        long long r_w = 0, r_m = 0;
+        long long r_w = 0, r_m = 0, o_sync = 0, o_mbox = 0, o_ld = 0, o_out = 0;
         int it = 0;
         unsigned nsl = 0;  // running slice number: D2 buffer nsl & 1, phase (nsl >> 1) & 1
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
@@ -757,87 +772,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const int c = cg * kTcCh + e * 32 + lane;
             const uint32_t par = it & 1;
             float *outp = p.out + (size_t)t * kTcOut * p.C + c;
-            float qin0 = 0.f, qin1 = 0.f;
             float m_peak = 0.f;
             double m_sumsq = 0.0;
             const bool meter = p.meter_peak != nullptr;
-            const long long k5 = clk();
+            const long long k5 = (PROF ? clk() : 0ll);
 #pragma unroll 1
             for (int s = 0; s < kRsSlices; s++, nsl++) {
                 const uint32_t b = nsl & 1u;
-                const long long k6 = clk();
-                mbar_wait(&d2_full[b], (nsl >> 1) & 1u);
-                if (s == 0) {
-                    mbar_wait(&mbox_ready[e], par);
-                    mbar_wait(&state_ready[e], par);
-                    qin0 = sstate[(e * 2 + 0) * 32 + lane];
-                    qin1 = sstate[(e * 2 + 1) * 32 + lane];
-                }
-                r_w += clk() - k6;
+                const long long k6 = (PROF ? clk() : 0ll);
+                if (warp == 18) mbar_wait(&d2_full[b], (nsl >> 1) & 1u);
+                const long long g0 = (PROF ? clk() : 0ll);
+                asm volatile("bar.sync 5, 256;" ::: "memory");
+                o_sync += (PROF ? clk() : 0ll) - g0;
+                if (s == 0) mbar_wait(&mbox_ready[e], par);
+                const long long k7 = (PROF ? clk() : 0ll);
+                r_w += k7 - k6;
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                // true state at the start of the four blocks this slice reads: zero-state part from the mailbox
-                // plus the response to the incoming state of the tile
-                uint32_t zs[8];
+                // true state at the start of the four blocks this slice reads, and this warp's 16 accumulator columns
+                uint32_t zs[8], e16[16], x16[16];
                 tmem_ld8(tmem_base + lane_base + kColMbox + 4 * s, zs);
+                tmem_ld16(tmem_base + lane_base + kColD2 + 64 * b + 16 * hsel, e16);
+                tmem_ld16(tmem_base + lane_base + kColD2 + 64 * b + 32 + 16 * hsel, x16);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (s == kRsSlices - 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&mbox_free[e]);
-                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                asm volatile("bar.sync 5, 256;" ::: "memory");
+                if (warp == 18 && lane == 0) mbar_arrive(&d2_empty[b]);
+                if (s == kRsSlices - 1 && lane == 0) mbar_arrive(&mbox_free[e]);
+                const long long k9 = (PROF ? clk() : 0ll);
+                o_ld += k9 - k7;
                 float sb[8];
-                const int fi = first ? 1 : 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const bool valid = 2 * s + k < kTcBlocks;  // the last slice reads three blocks
-                    const float *M = p.Mb[fi][valid ? 2 * s + k : 0];
-                    const float v0 = fmaf(M[0], qin0, fmaf(M[1], qin1, __uint_as_float(zs[2 * k])));
-                    const float v1 = fmaf(M[2], qin0, fmaf(M[3], qin1, __uint_as_float(zs[2 * k + 1])));
-                    sb[2 * k] = valid ? v0 : 0.f;
-                    sb[2 * k + 1] = valid ? v1 : 0.f;
-                }
-                const unsigned char *rcb = stage + (((first && s == 0) ? kTcRcFirst : kRsN * s) >> 3) * kKbStride;
-                float *op = outp + (size_t)(kRsN * s) * p.C;
-                // compact loop (4 outputs per trip): the kernel's hot code has to stay inside the instruction cache
-                const int ng = (s == kRsSlices - 1) ? (kTcOut - kRsN * (kRsSlices - 1) + 3) / 4 : kRsN / 4;
-#pragma unroll 1
-                for (int g = 0; g < ng; g++) {
-                    uint32_t e4[4], x4[4];
-                    tmem_ld4(tmem_base + lane_base + kColD2 + 64 * b + 4 * g, e4);
-                    tmem_ld4(tmem_base + lane_base + kColD2 + 64 * b + 32 + 4 * g, x4);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    const unsigned char *rcg = rcb + (g >> 1) * kKbStride + (g & 1) * 8 * kMbStride + 128;
+                for (int k = 0; k < 8; k++) sb[k] = __uint_as_float(zs[k]);
+                const int nout = ((s == kRsSlices - 1) ? kTcOut - kRsN * (kRsSlices - 1) : kRsN) - 16 * hsel;
+                const unsigned char *rcg = stage + ((((first && s == 0) ? kTcRcFirst : kRsN * s) >> 3) + 2 * hsel) * kKbStride + 128;
+                float *op = outp + (size_t)(kRsN * s + 16 * hsel) * p.C;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float4 ca = *reinterpret_cast<const float4 *>(rcg + (2 * i) * kMbStride);
-                        const float4 cb = *reinterpret_cast<const float4 *>(rcg + (2 * i + 1) * kMbStride);
-                        const float c0 = fmaf(ca.y, sb[1], ca.x * sb[0]), c1 = fmaf(ca.w, sb[3], ca.z * sb[2]);
-                        const float c2 = fmaf(cb.y, sb[5], cb.x * sb[4]), c3 = fmaf(cb.w, sb[7], cb.z * sb[6]);
-                        const float o = fmaf(__uint_as_float(e4[i]) + __uint_as_float(x4[i]), p.descale_rs, (c0 + c1) + (c2 + c3));
-                        if (kRsN * s + 4 * g + i < kTcOut) {
-                            *op = o;
-                            if (meter) {
-                                m_peak = fmaxf(m_peak, fabsf(o));
-                                m_sumsq += (double)o * (double)o;
-                            }
+                for (int i = 0; i < 16; i++) {
+                    const unsigned char *rci = rcg + (i >> 3) * kKbStride + 2 * (i & 7) * kMbStride;
+                    const float4 ca = *reinterpret_cast<const float4 *>(rci);
+                    const float4 cb = *reinterpret_cast<const float4 *>(rci + kMbStride);
+                    const float c0 = fmaf(ca.y, sb[1], ca.x * sb[0]), c1 = fmaf(ca.w, sb[3], ca.z * sb[2]);
+                    const float c2 = fmaf(cb.y, sb[5], cb.x * sb[4]), c3 = fmaf(cb.w, sb[7], cb.z * sb[6]);
+                    const float o = fmaf(__uint_as_float(e16[i]) + __uint_as_float(x16[i]), p.descale_rs, (c0 + c1) + (c2 + c3));
+                    if (i < nout) {
+                        op[(size_t)i * p.C] = o;
+                        if (meter) {
+                            m_peak = fmaxf(m_peak, fabsf(o));
+                            m_sumsq += (double)o * (double)o;
                         }
-                        op += p.C;
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d2_empty[b]);
+                o_out += (PROF ? clk() : 0ll) - k9;
             }
-            r_m += clk() - k5;
+            r_m += (PROF ? clk() : 0ll) - k5;
             if (meter) {
                 atomic_max_nonneg(p.meter_peak + c, (double)m_peak);
                 atomicAdd(p.meter_sumsq + c, m_sumsq);
             }
         }
-        if (p.prof && warp == 18 && lane == 0) {
+        if (PROF && p.prof && warp == 18 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
             pr[kProfOutWait] = r_w;
             pr[kProfOutMain] = r_m;
+            pr[kProfChunk0 + 0] = o_sync;
+            pr[kProfChunk0 + 1] = o_mbox;
+            pr[kProfChunk0 + 2] = o_ld;
+            pr[kProfChunk0 + 3] = o_out;
         }
     } else {
         // ================================ MMA2 issuer =================================
@@ -855,10 +855,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 for (int s = 0; s < kRsSlices; s++, nsl++) {
                     const uint32_t b = nsl & 1u;
                     const int nch = (s == kRsSlices - 1) ? 3 : 4;
-                    const long long c0 = clk();
+                    const long long c0 = (PROF ? clk() : 0ll);
                     mbar_wait(&a2_ready[2 * s + nch - 1], it & 1);  // each drain role stages its blocks (even / odd) in order
                     mbar_wait(&a2_ready[2 * s + nch - 2], it & 1);
-                    w_y += clk() - c0;
+                    w_y += (PROF ? clk() : 0ll) - c0;
                     mbar_wait(&d2_empty[b], ((nsl >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t dE = tmem_base + kColD2 + 64 * b, dX = dE + kRsN;
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     __syncwarp();
                 }
             }
-            if (p.prof && lane == 0) p.prof[blockIdx.x * kProfCount + kProfMma2Wait] = w_y;
+            if (PROF && p.prof && lane == 0) p.prof[blockIdx.x * kProfCount + kProfMma2Wait] = w_y;
         }
     }
 
