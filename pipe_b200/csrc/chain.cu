@@ -460,7 +460,10 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         p.AL_first[i] = s.tc_ALf[i];
         p.A16[i] = s.tc_A16[i];
     }
-    memcpy(p.Wz, s.tc_Wz, sizeof(p.Wz));
+    for (int i = 0; i < 16; i++) {  // applied to the raw accumulator sum: fold fscale in
+        p.Wz[i][0] = (float)((double)s.tc_Wz[i][0] * (double)p.fscale);
+        p.Wz[i][1] = (float)((double)s.tc_Wz[i][1] * (double)p.fscale);
+    }
     memcpy(p.Mb, s.tc_Mb, sizeof(p.Mb));
     p.rc = (const float *)s.d_tc_rc;
     if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);

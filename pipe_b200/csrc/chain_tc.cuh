@@ -66,7 +66,7 @@ constexpr int kTcLead = 272;        // frames of the window before the tile star
 constexpr int kTcMaxTaps = 257;
 constexpr int kTcCores = 75;        // Toeplitz core matrices per piece
 constexpr int kTcThreads = 864;     // 27 warps: TMA, MMA1, 2x4 converters, 2x4 drain, 2x4 output, MMA2
-constexpr int kRawStages = 6, kCvtStages = 3;
+constexpr int kRawStages = 5, kCvtStages = 3;
 constexpr int kTcRing = 8;          // chunks of the MMA2 A operand kept in shared memory (block b lives in slot b % 8)
 constexpr int kTcBlocks = kTcN / 16;     // 11 blocks of 16 rows: biquad blocks == K chunks of MMA2
 constexpr int kTcFirstDone = 17;    // column block b of D1 is complete after chunk b + 17 (the last two after chunk 26)
@@ -112,7 +112,7 @@ struct TcParams {
     double A16[4];       // block step
     double AL[4];        // A^160: look-back step, incoming state -> state after row 159
     double AL_first[4];  // A^145: the same for tile 0, whose state enters at row 15
-    float Wz[16][2];     // zero-state end state of a block: Z = sum_i Wz[i] * f_i (on the grid), Wz[i] = A^(15-i) B / 2^10
+    float Wz[16][2];     // zero-state end state of a block: Z = sum_i Wz[i] * (E+X)_i, Wz[i] = A^(15-i) B * fscale / 2^10
     float Mb[2][kTcBlocks][4];     // [0]: A^(16 b), incoming state -> state at the start of block b;
                                    // [1]: tile 0: identity for b = 0 (the state enters at row 15), A^(16 b - 15) after
 };
@@ -264,10 +264,10 @@ constexpr int kTabBytes = TcTables::kBytes;                     // 38400 + 40960
 constexpr int kMbStride = 144, kKbStride = 16 * kMbStride, kPieceBytes = 2 * kKbStride, kChunkBytes = 2 * kPieceBytes;
 constexpr int kOffStage = ((kOffTab + kTabBytes + 127) / 128) * 128;
 constexpr int kStageBytes = kTcRing * kChunkBytes;              // 73728
-constexpr int kOffSstate = kOffStage + kStageBytes;             // [4][2][32] float: incoming state of the tile
-constexpr int kOffBar = kOffSstate + 4 * 2 * 32 * 4;
+constexpr int kOffZx = kOffStage + kStageBytes;                 // [11][2][128] float: zero-state end state Z_b of every block
+constexpr int kOffBar = kOffZx + kTcBlocks * 2 * kTcCh * 4;
 constexpr int kNumBlkBars = kTcChunks - kTcFirstDone;           // 10: one per chunk 17..26
-constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + 1 + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 4 + 2;
+constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + kTcBlocks + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 4 + 2;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
@@ -294,15 +294,18 @@ __device__ __forceinline__ void ep_block(const uint32_t (&re)[16], const uint32_
     using namespace tc;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        float a = (__uint_as_float(re[i]) + __uint_as_float(rx[i])) * p.fscale;
-        if (FIRST0 && i < kTcHr) a = yh[(size_t)i * p.C] * p.yh_scale;
-        const float ra = (a + 12582912.f) - 12582912.f;  // nearest integer (|a| < 2^22)
-        const __half h0 = __float2half_rn(ra);            // above 2048 the fp16 grid is coarser than 1:
-        const __half h1 = __float2half_rn(a - __half2float(h0));  // the remainder is taken from what h0 really holds
-        vmax = fmaxf(vmax, fabsf(a));
-        if (!FIRST0 || i >= kTcHr) {
-            p0 = fmaf(p.Wz[i][0], a, p0);
-            p1 = fmaf(p.Wz[i][1], a, p1);
+        float t = __uint_as_float(re[i]) + __uint_as_float(rx[i]), sc = p.fscale;
+        if (FIRST0 && i < kTcHr) {
+            t = yh[(size_t)i * p.C];
+            sc = p.yh_scale;
+        }
+        const float ra = fmaf(t, sc, 12582912.f) - 12582912.f;  // t * sc to the nearest integer (|.| < 2^22)
+        const __half h0 = __float2half_rn(ra);                   // above 2048 the fp16 grid is coarser than 1:
+        const __half h1 = __float2half_rn(fmaf(t, sc, -__half2float(h0)));  // the remainder is taken from what h0 really holds
+        vmax = fmaxf(vmax, fabsf(ra));
+        if (!FIRST0 || i >= kTcHr) {  // Wz is pre-multiplied by fscale
+            p0 = fmaf(p.Wz[i][0], t, p0);
+            p1 = fmaf(p.Wz[i][1], t, p1);
         }
         *reinterpret_cast<__half *>(dst + (i >> 3) * kKbStride + (i & 7) * 16) = h0;
         *reinterpret_cast<__half *>(dst + (i >> 3) * kKbStride + (i & 7) * 16 + kPieceBytes) = h1;
@@ -319,12 +322,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     unsigned char *cvt = smem + kOffCvt;
     __half *tab = reinterpret_cast<__half *>(smem + kOffTab);
     unsigned char *stage = smem + kOffStage;
+    float *zx = reinterpret_cast<float *>(smem + kOffZx);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
     uint64_t *raw_full = bars, *raw_empty = bars + kRawStages;
     uint64_t *cvt_full = bars + 2 * kRawStages, *cvt_empty = cvt_full + kCvtStages;
     uint64_t *blk_full = cvt_empty + kCvtStages;    // [10] MMA1 (commit after chunk 17+i) -> drain: column block i of D1 is final
-    uint64_t *tmem_empty = blk_full + kNumBlkBars;  //      drain warps -> MMA1: D1 has been read
-    uint64_t *a2_ready = tmem_empty + 1;            // [11] drain warps -> MMA2: the f pieces of block b are in the staging tile
+    uint64_t *d1_free = blk_full + kNumBlkBars;     // [11] drain warps -> MMA1: column block b of D1 has been read (the next tile may overwrite it)
+    uint64_t *a2_ready = d1_free + kTcBlocks;            // [11] drain warps -> MMA2: the f pieces of block b are in the staging tile
     uint64_t *stage_free = a2_ready + kTcBlocks;    //      MMA2 (commit) -> drain: the staging tile has been consumed
     uint64_t *d2_full = stage_free + 1;             // [2]  MMA2 (commit) -> output warps
     uint64_t *d2_empty = d2_full + 2;               // [2]  output warps -> MMA2
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&cvt_empty[i], 1);
         }
         for (int i = 0; i < kNumBlkBars; i++) mbar_init(&blk_full[i], 1);
-        mbar_init(tmem_empty, 8);
+        for (int i = 0; i < kTcBlocks; i++) mbar_init(&d1_free[i], 1);
         for (int i = 0; i < kTcBlocks; i++) mbar_init(&a2_ready[i], 1);
         mbar_init(stage_free, 1);
         for (int i = 0; i < 2; i++) {
@@ -427,25 +431,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             long long w_t = 0, w_c = 0, w_i = 0;
             const long long kstart = (PROF ? clk() : 0ll);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                long long c0 = (PROF ? clk() : 0ll);
-                mbar_wait(tmem_empty, tph ^ 1);  // the previous tile's D1 has been read
-                w_t += (PROF ? clk() : 0ll) - c0;
-                asm volatile("tcgen05.fence::after_thread_sync;");
                 static_assert(kTcChunks % kCvtStages == 0, "the chunk loop is unrolled by the number of A stages");
 #pragma unroll 3
                 for (int q = 0; q < kTcChunks; q++) {
-                    // everything here is warp-uniform arithmetic on the loop counter
-                    int nb0 = 0, nbl = kTcN / 8;
-                    if (q > 0) {
-                        int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
-                        if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
-                        nb0 = lo;
-                        nbl = hi - lo + 1;
-                    }
-                    const uint4 qc = make_uint4((uint32_t)((52 - 2 * q + nb0) * 128) >> 4, make_idesc(8 * nbl), (uint32_t)(8 * nb0), 0u);
+                    // Window of chunk q in 8-column blocks: [lo, hi], widened to an even count.  For q <= 10 its last two blocks
+                    // (2q, 2q+1) are touched for the first time in this tile: they are written with accumulate = 0 by a
+                    // separate N = 16 instruction, so D1 never needs zeroing and the previous tile's drain only has to have
+                    // released column block q (16 columns) before chunk q -- MMA1 of the next tile overlaps the drain's tail.
+                    int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
+                    if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
+                    const bool has_new = q < kTcBlocks;           // blocks 2q, 2q+1 are new
+                    const int n_old = has_new ? 2 * q : hi - lo + 1;  // 8-column blocks that already hold partial sums
+                    const uint32_t toff = (uint32_t)((52 - 2 * q + lo) * 128) >> 4;
                     const uint64_t a0 = ad0 + (uint64_t)(s * (kCvtStageBytes >> 4)), a1 = a0 + (4096 >> 4);
-                    const uint64_t b0 = bd0 + qc.x, b1 = bd1 + qc.x, b2 = bd2 + qc.x, b3 = bd3 + qc.x;
-                    const uint32_t dE = tmem_base + kColE + qc.z, dX = tmem_base + kColX + qc.z;
+                    const uint64_t b0 = bd0 + toff, b1 = bd1 + toff, b2 = bd2 + toff, b3 = bd3 + toff;
+                    const uint32_t dE = tmem_base + kColE + 8 * lo, dX = tmem_base + kColX + 8 * lo;
+                    long long c0 = (PROF ? clk() : 0ll);
+                    if (has_new && tph) mbar_wait(&d1_free[q], (tph - 1) & 1);  // tph counts this CTA's tiles
+                    w_t += (PROF ? clk() : 0ll) - c0;
                     c0 = (PROF ? clk() : 0ll);
                     mbar_wait(&cvt_full[s], ph);
                     const long long c1 = (PROF ? clk() : 0ll);
@@ -453,10 +456,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (elect_one()) {
                         if (!(p.dbg & 1)) {
-                            umma(dE, a0, b0, qc.y, q > 0);   // x0 h0: exact, integers < 2^24
-                            umma(dX, a0, b1, qc.y, q > 0);   // x0 (h1 + h2): the tap's remainder in two pieces
-                            umma(dX, a0, b2, qc.y, 1);
-                            umma(dX, a1, b3, qc.y, 1);       // x1 h: |x1| <= 1/2, the tap rounded once (2^-12 relative) is enough
+                            if (n_old > 0) {
+                                const uint32_t idn = make_idesc(8 * n_old);
+                                umma(dE, a0, b0, idn, 1);   // x0 h0: exact, integers < 2^24
+                                umma(dX, a0, b1, idn, 1);   // x0 (h1 + h2): the tap's remainder in two pieces
+                            }
+                            if (has_new) {
+                                const uint32_t idn = make_idesc(16), off = (uint32_t)(n_old * 128) >> 4;
+                                umma(dE + 8 * n_old, a0, b0 + off, idn, 0);
+                                umma(dX + 8 * n_old, a0, b1 + off, idn, 0);
+                            }
+                            const uint32_t idw = make_idesc(8 * (hi - lo + 1));
+                            umma(dX, a0, b2, idw, 1);
+                            umma(dX, a1, b3, idw, 1);       // x1 h: |x1| <= 1/2, the tap rounded once (2^-12 relative) is enough
                         }
                         umma_commit(&cvt_empty[s]);  // frees the A stage when these MMAs have read it
                         if (q >= kTcFirstDone) umma_commit(&blk_full[q - kTcFirstDone]);  // column block q-17 (after 26: 9 and 10) is final
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     w_i += c2 - c1;
                     if (++s == kCvtStages) { s = 0; ph ^= 1; }
                 }
-                tph ^= 1;
+                tph++;
             }
             if (PROF && p.prof && lane == 0) {
                 long long *pr = p.prof + blockIdx.x * kProfCount;
@@ -516,14 +528,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 __half2 hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const float a = v[2 * i] * sc, b = v[2 * i + 1] * sc;
-                    // round to nearest integer on the FMA pipe (exact for |a| < 2^22; larger values trip the range check)
-                    const float ra = (a + 12582912.f) - 12582912.f, rb = (b + 12582912.f) - 12582912.f;
+                    // x * scale rounded to the nearest integer on the FMA pipe (|.| < 2^22; larger values trip the range check),
+                    // and the remainder with a single rounding
+                    const float ra = fmaf(v[2 * i], sc, 12582912.f) - 12582912.f, rb = fmaf(v[2 * i + 1], sc, 12582912.f) - 12582912.f;
                     hi[i] = __floats2half2_rn(ra, rb);
-                    lo[i] = __floats2half2_rn(a - ra, b - rb);
-                    vmax = fmaxf(vmax, fmaxf(fabsf(a), fabsf(b)));
-                    v[2 * i] = a;
-                    v[2 * i + 1] = b;
+                    lo[i] = __floats2half2_rn(fmaf(v[2 * i], sc, -ra), fmaf(v[2 * i + 1], sc, -rb));
+                    vmax = fmaxf(vmax, fmaxf(fabsf(ra), fabsf(rb)));
                 }
                 const int off = (1 - kb) * 2048 + mb * 128 + fr_i * 16;  // K-blocks swapped (Toeplitz trick)
                 *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<uint4 *>(hi);
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 if (last && hrow >= 0) {
                     // carried FIR input history: frames [n-hist_rows, n) in gain-scaled units (K1's convention)
                     float *hp = p.xhist_next + (size_t)hrow * p.C + cg * kTcCh + mb * 8;
-                    const float is = p.inv_scale_in;
+                    const float is = sc * p.inv_scale_in;
                     *reinterpret_cast<float4 *>(hp) = make_float4(v[0] * is, v[1] * is, v[2] * is, v[3] * is);
                     *reinterpret_cast<float4 *>(hp + 4) = make_float4(v[4] * is, v[5] * is, v[6] * is, v[7] * is);
                 }
@@ -597,38 +607,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 if (first && b == 0) ep_block<true>(re, rx, dst, p, yh, p0, p1, vmax);
                 else ep_block<false>(re, rx, dst, p, yh, p0, p1, vmax);
                 if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+                asm volatile("tcgen05.fence::before_thread_sync;");
                 group_sync(gid);
-                if (gl && lane == 0) mbar_arrive(&a2_ready[b]);
-                // Z_b goes to role A through the first two E columns of the block itself: they are dead until the next tile's MMA1
-                tmem_st2(tmem_base + lane_base + kColE + 16 * b, __float_as_uint(p0), __float_as_uint(p1));
+                if (gl && lane == 0) {
+                    mbar_arrive(&a2_ready[b]);
+                    mbar_arrive(&d1_free[b]);  // all four quadrants have read the block's columns
+                }
+                zx[(2 * b + 0) * kTcCh + e * 32 + lane] = p0;
+                zx[(2 * b + 1) * kTcCh + e * 32 + lane] = p1;
                 e_m += (PROF ? clk() : 0ll) - k1;
             }
             const long long k4 = (PROF ? clk() : 0ll);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             if (roleB) {
-                asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&zx_ready[e]);
-                    mbar_arrive(tmem_empty);  // this warp is done with D1 (role A still reads the Z columns: it arrives after that)
-                }
+                if (lane == 0) mbar_arrive(&zx_ready[e]);
                 e_l += (PROF ? clk() : 0ll) - k4;
                 continue;
             }
             // ---- role A: block-state recursion in double, s(b+1) = A^16 s(b) + Z_b from a zero state; the mailbox entries
             //      Z_b are replaced by the state at the START of block b (float) for the output warp
             mbar_wait(&zx_ready[e], par);
-            asm volatile("tcgen05.fence::after_thread_sync;");
             double s10_1 = 0.0, s10_2 = 0.0;  // zero-state state after row 159
             float szs[kTcBlocks][2];          // zero-state state at the start of each block
             {
                 uint32_t z[kTcBlocks][2];
 #pragma unroll
-                for (int b = 0; b < kTcBlocks; b++) tmem_ld2(tmem_base + lane_base + kColE + 16 * b, z[b][0], z[b][1]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty);  // D1 may be overwritten
+                for (int b = 0; b < kTcBlocks; b++) {
+                    z[b][0] = __float_as_uint(zx[(2 * b + 0) * kTcCh + e * 32 + lane]);
+                    z[b][1] = __float_as_uint(zx[(2 * b + 1) * kTcCh + e * 32 + lane]);
+                }
                 double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int b = 0; b < kTcBlocks; b++) {
