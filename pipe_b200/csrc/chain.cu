@@ -52,6 +52,8 @@ struct Segment {
     double tc_A16[4], tc_ALf[4];                     // A^16, A^145
     float tc_Wz[16][2];
     float tc_Mb[2][kTcBlocks][4];
+    double tc_Wb[4], tc_Wbi[4];
+    bool tc_level_ok = true;                         // the biquad keeps the broadband level (see build_tc_tables)
     std::vector<float> tc_rc;                        // [147 + 32][8] output correction per block state (see chain_tc.cuh)
 };
 
@@ -244,6 +246,20 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 T3[idx] = __float2half_rn((float)(gtap(8 * e + n_i - k_i + 1) * sh));
             }
     PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    // K2's fixed-point grids make its error relative to the level INSIDE the chain (FIR output at full scale), because the
+    // biquad is folded into the resampler matrix P.  A biquad that removes most of a broadband signal (a 120 Hz low-pass on
+    // white noise: -29 dB) would leave that error standing against a much smaller output, so such chains stay on K1:
+    // the L2 norm of the biquad's impulse response (its gain for white input) must be at least -6 dB.
+    {
+        double s1 = 0, s2 = 0, e2 = 0;
+        for (int n = 0; n < 1 << 14; n++) {
+            const double x = n == 0 ? 1.0 : 0.0, y = s.b[0] * x + s1;
+            s1 = s.b[1] * x - s.a[0] * y + s2;
+            s2 = s.b[2] * x - s.a[1] * y;
+            e2 += y * y;
+        }
+        s.tc_level_ok = std::isfinite(e2) && std::sqrt(e2) >= 0.5;
+    }
     // MMA2: P = blockdiag(G16) * R.  R[row][m] = coef[branch(m)][i_m - row] is the polyphase matrix of one tile (row = frame + 15;
     // output m is triggered by tile-relative frame i_m = ceil((m+1)*160/147) - 1 with branch 146 - ((i_m+1)*147 % 160)); G16 is the
     // biquad's zero-state response inside a block of 16 rows: y[r'] = sum_{r <= r', same block} g[r'-r] f[r], g[0] = b0,
@@ -323,10 +339,48 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     }
     PB_CUDA(cudaMemcpy((char *)s.d_tc_tables + (size_t)TcTables::kHalfs * 2, b2.data(), b2.size() * sizeof(__half),
                        cudaMemcpyHostToDevice));
-    // Block states.  The response of output m to the true state at the start of block b is
-    //   rc[m][2k..2k+1] = g_bq g_out sum_{rows r of block b} R[r][m] (A^(r-16b))[0][.],   b = 2 (m/32) + k, k = 0..3;
-    // tile 0, block 0: the state enters at row 15.
+    // Block states.  The free response of a block to the state s at its start is y_sr[i] = (A^i s)[0], i = 0..15: a 16 x 2
+    // matrix H.  With H = U S V^T the states travel as w = W s, W = S V^T ("balanced" coordinates): y_sr = U w with
+    // orthonormal U, so neither the tables below nor the float arithmetic on w see the cancellation that the TDF-II basis
+    // has for poles near the unit circle.  The response of output m to w at the start of block b is
+    //   rc[m][2k..2k+1] = g_bq g_out sum_{rows i of block b} R[16b+i][m] U[i][.],   b = 2 (m/32) + k, k = 0..3;
+    // tile 0, block 0: the state enters at row 15 (only U[0][.] applies, to row 15).
     {
+        double H[16][2], G[3] = {0, 0, 0};  // G = H^T H
+        for (int i = 0; i < 16; i++) {
+            H[i][0] = Apow[i][0];
+            H[i][1] = Apow[i][1];
+            G[0] += H[i][0] * H[i][0];
+            G[1] += H[i][0] * H[i][1];
+            G[2] += H[i][1] * H[i][1];
+        }
+        // eigen-decomposition of the symmetric 2x2 G: V (columns), S^2
+        const double th = 0.5 * std::atan2(2.0 * G[1], G[0] - G[2]);
+        const double cs = std::cos(th), sn = std::sin(th);
+        const double V[2][2] = {{cs, -sn}, {sn, cs}};
+        double S[2];
+        for (int q = 0; q < 2; q++) {
+            double n2 = 0;
+            for (int i = 0; i < 16; i++) {
+                const double v = H[i][0] * V[0][q] + H[i][1] * V[1][q];
+                n2 += v * v;
+            }
+            S[q] = std::sqrt(n2);
+            if (!(S[q] > 1e-300)) S[q] = 1e-300;
+        }
+        double U[16][2], W[4], Wi[4];
+        for (int i = 0; i < 16; i++)
+            for (int q = 0; q < 2; q++) U[i][q] = (H[i][0] * V[0][q] + H[i][1] * V[1][q]) / S[q];
+        for (int q = 0; q < 2; q++) {
+            W[2 * q] = S[q] * V[0][q];       // w_q = S_q (V^T s)_q
+            W[2 * q + 1] = S[q] * V[1][q];
+            Wi[q] = V[0][q] / S[q];          // s = V S^-1 w
+            Wi[2 + q] = V[1][q] / S[q];
+        }
+        for (int i = 0; i < 4; i++) {
+            s.tc_Wb[i] = W[i];
+            s.tc_Wbi[i] = Wi[i];
+        }
         const double gg = s.g[2] * s.g[3];
         s.tc_rc.assign((size_t)kTcRcRows * 8, 0.f);
         for (int m = 0; m < kTcOut; m++)
@@ -334,8 +388,8 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 double v0 = 0, v1 = 0;
                 for (int i = 0; i < 16; i++) {
                     const double r = rtap(16 * b + i, m);
-                    v0 += r * Apow[i][0];
-                    v1 += r * Apow[i][1];
+                    v0 += r * U[i][0];
+                    v1 += r * U[i][1];
                 }
                 const int k = b - 2 * (m / kRsN);
                 if (k >= 0 && k < 4) {
@@ -347,22 +401,33 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
             }
         for (int m = 0; m < kRsN; m++) {
             for (int q = 0; q < 8; q++) s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + q] = s.tc_rc[(size_t)m * 8 + q];
-            s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 0] = (float)(rtap(kTcHr, m) * gg);  // block 0: only row 15, (A^0)[0] = [1 0]
-            s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 1] = 0.f;
+            s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 0] = (float)(rtap(kTcHr, m) * U[0][0] * gg);  // block 0: only row 15, y_sr = U[0] w
+            s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 1] = (float)(rtap(kTcHr, m) * U[0][1] * gg);
         }
         PB_CUDA(cudaMemcpy(s.d_tc_rc, s.tc_rc.data(), s.tc_rc.size() * sizeof(float), cudaMemcpyHostToDevice));
-        for (int b = 0; b < kTcBlocks; b++)
+        auto sim = [&](const double *M, double *out) {  // W M W^-1
+            double t[4] = {W[0] * M[0] + W[1] * M[2], W[0] * M[1] + W[1] * M[3], W[2] * M[0] + W[3] * M[2], W[2] * M[1] + W[3] * M[3]};
+            out[0] = t[0] * Wi[0] + t[1] * Wi[2];
+            out[1] = t[0] * Wi[1] + t[1] * Wi[3];
+            out[2] = t[2] * Wi[0] + t[3] * Wi[2];
+            out[3] = t[2] * Wi[1] + t[3] * Wi[3];
+        };
+        for (int b = 0; b < kTcBlocks; b++) {
+            double m0[4], m1[4];
+            sim(Apow[16 * b], m0);
+            if (b == 0) { m1[0] = 1; m1[1] = 0; m1[2] = 0; m1[3] = 1; }
+            else sim(Apow[16 * b - kTcHr], m1);
             for (int i = 0; i < 4; i++) {
-                s.tc_Mb[0][b][i] = (float)Apow[16 * b][i];
-                s.tc_Mb[1][b][i] = (float)(b == 0 ? (i == 0 || i == 3 ? 1.0 : 0.0) : Apow[16 * b - kTcHr][i]);
+                s.tc_Mb[0][b][i] = (float)m0[i];
+                s.tc_Mb[1][b][i] = (float)m1[i];
             }
-        for (int i = 0; i < 4; i++) {
-            s.tc_A16[i] = Apow[16][i];
-            s.tc_ALf[i] = Apow[kTcFrames - kTcHr][i];
         }
-        for (int i = 0; i < 16; i++) {
-            s.tc_Wz[i][0] = (float)((Apow[15 - i][0] * B[0] + Apow[15 - i][1] * B[1]) / 1024.0);
-            s.tc_Wz[i][1] = (float)((Apow[15 - i][2] * B[0] + Apow[15 - i][3] * B[1]) / 1024.0);
+        sim(Apow[16], s.tc_A16);  // block step in balanced coordinates
+        for (int i = 0; i < 4; i++) s.tc_ALf[i] = Apow[kTcFrames - kTcHr][i];
+        for (int i = 0; i < 16; i++) {  // W A^(15-i) B / grid
+            const double z0 = Apow[15 - i][0] * B[0] + Apow[15 - i][1] * B[1], z1 = Apow[15 - i][2] * B[0] + Apow[15 - i][3] * B[1];
+            s.tc_Wz[i][0] = (float)((W[0] * z0 + W[1] * z1) / 2048.0);
+            s.tc_Wz[i][1] = (float)((W[2] * z0 + W[3] * z1) / 2048.0);
         }
     }
     return PB_OK;
@@ -448,7 +513,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     p.scale_in = (float)(s.g[0] * sx);
     p.scale_hist = (float)sx;
     p.inv_scale_in = (float)(1.0 / sx);
-    const double sf = 1024.0;  // grid of the FIR output pieces
+    const double sf = 2048.0;  // grid of the FIR output pieces (values beyond +-1 keep an exact remainder, see ep_block)
     p.fscale = (float)(s.g[1] * sf / (sx * std::ldexp(1.0, s.tc_sh)));
     p.inv_fgrid = (float)(1.0 / sf);
     p.yh_scale = (float)(sf / s.g[2]);
@@ -465,6 +530,10 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         p.Wz[i][1] = (float)((double)s.tc_Wz[i][1] * (double)p.fscale);
     }
     memcpy(p.Mb, s.tc_Mb, sizeof(p.Mb));
+    for (int i = 0; i < 4; i++) {
+        p.Wb[i] = s.tc_Wb[i];
+        p.Wbi[i] = s.tc_Wbi[i];
+    }
     p.rc = (const float *)s.d_tc_rc;
     if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int total = p.n_tiles * p.n_cg;
@@ -757,7 +826,7 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
             const bool lastseg = (i + 1 == c->segs.size());
             void *dst = lastseg ? out_dev : c->d_mid[i & 1];
             // K2 needs the call aligned to 160-frame tiles (then the resampler phase is 0 at every tile start)
-            const bool use_tc = s.tc_ok && s.acc == 0 && n >= kTcFrames && n % kTcFrames == 0 && s.g[2] != 0.0 && s.b[0] == s.b[0] &&
+            const bool use_tc = s.tc_ok && s.acc == 0 && n >= kTcFrames && n % kTcFrames == 0 && s.g[2] != 0.0 && s.tc_level_ok &&
                                 ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
             int32_t r = use_tc ? launch_segment_tc(c, s, src, n, dst, lastseg, stream)
                         : c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, src, n, dst, lastseg, stream)
@@ -961,7 +1030,7 @@ extern "C" int32_t pb_chain_sync(pb_chain *c, void *stream)
     PB_CUDA(cudaStreamSynchronize(c->st_compute));
     int flag = 0;
     PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fp16 fixed-point range (|g*x| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
+    if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fixed-point range of the fp16 split (|g*x| > 1, or |y| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
                                                     : "fused kernel: look-back wait timed out (kernel error flag set)");
     return PB_OK;
 }
@@ -1059,7 +1128,7 @@ extern "C" int32_t pb_chain_collect(pb_chain *c, int64_t *buf_out_frames, int32_
     {
         int flag = 0;
         PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
-        if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fp16 fixed-point range (|g*x| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
+        if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fixed-point range of the fp16 split (|g*x| > 1, or |y| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
                                                         : "fused kernel: look-back wait timed out (kernel error flag set)");
     }
     if (sl.user_out && sl.out_frames) memcpy(sl.user_out, sl.h_out, c->elem * (size_t)sl.out_frames * c->C);

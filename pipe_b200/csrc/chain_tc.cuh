@@ -29,7 +29,7 @@
 //   grid, which summed over 257 taps was 5.7e-7 of the peak).  x0*h0 goes to accumulator E: every product
 //   and every partial sum is an integer below 2^24, so E is EXACT.  x0*h1 + x0*h2 + x1*h0 + x1*h1 go to
 //   accumulator X, 2^-9 of E in magnitude, whose truncation is negligible.  Modelled FIR error 6e-8.
-//   MMA2 uses the same scheme with two pieces each (f*2^10 = f0 + f1, P*2^sh2 = p0 + p1; at most 32 rows per
+//   MMA2 uses the same scheme with two pieces each (f*2^11 = f0 + f1, P*2^sh2 = p0 + p1; at most 32 rows per
 //   output): E2 = f0*p0 exact, X2 = f0*p1 + f1*p0 + f1*p1.  Modelled error 2.2e-7 of the peak.
 //
 // B operand of MMA1: the Toeplitz matrix is never materialised.  A K-major 8x8 core matrix depends only on
@@ -104,17 +104,18 @@ struct TcParams {
     float scale_in;      // g_load * 2^11 (applied to frames of this call)
     float scale_hist;    // 2^11          (history frames are already gain-scaled)
     float inv_scale_in;  // 2^-11: turns scaled input back into xhist_next values
-    float fscale;        // (E + X) -> FIR output on the 2^10 grid: g_fir * 2^10 / (2^11 * 2^sh)
-    float inv_fgrid;     // 2^-10
-    float yh_scale;      // 2^10 / g_bq: carried y history (tile 0, rows 0..14) -> the same grid, biquad gain undone
-    float descale_rs;    // g_bq * g_out / (2^10 * 2^sh2)
+    float fscale;        // (E + X) -> FIR output on the 2^11 grid: g_fir * 2^11 / (2^11 * 2^sh)
+    float inv_fgrid;     // 2^-11
+    float yh_scale;      // 2^11 / g_bq: carried y history (tile 0, rows 0..14) -> the same grid, biquad gain undone
+    float descale_rs;    // g_bq * g_out / (2^11 * 2^sh2)
     double b0, b1, b2, a1, a2, g_bq;
     double A16[4];       // block step
     double AL[4];        // A^160: look-back step, incoming state -> state after row 159
     double AL_first[4];  // A^145: the same for tile 0, whose state enters at row 15
-    float Wz[16][2];     // zero-state end state of a block: Z = sum_i Wz[i] * (E+X)_i, Wz[i] = A^(15-i) B * fscale / 2^10
-    float Mb[2][kTcBlocks][4];     // [0]: A^(16 b), incoming state -> state at the start of block b;
-                                   // [1]: tile 0: identity for b = 0 (the state enters at row 15), A^(16 b - 15) after
+    float Wz[16][2];     // zero-state end state of a block: Z = sum_i Wz[i] * (E+X)_i, Wz[i] = A^(15-i) B * fscale / 2^11
+    double Wb[4], Wbi[4];          // balanced state coordinates w = Wb s, s = Wbi w; A16 and Wz are given in them
+    float Mb[2][kTcBlocks][4];     // in those coordinates: [0]: W A^(16 b) W^-1, incoming state -> state at the start of block b;
+                                   // [1]: tile 0: identity for b = 0 (the state enters at row 15), W A^(16 b - 15) W^-1 after
 };
 
 // out[m] += sum_k rc[m][2k..2k+1] . s(block 2*(m/32) + k), k = 0..3; rows 147.. : tile 0, slice 0.  In global memory, copied at
@@ -284,7 +285,7 @@ constexpr uint32_t kColE = 0, kColX = 176, kColD2 = 352, kColMbox = 480;
 
 }  // namespace tc
 
-// One block of 16 FIR columns of one channel: f*2^10 = (E + X) * fscale -> pieces f0 (integer grid) + f1 in the A operand
+// One block of 16 FIR columns of one channel: f*2^11 = (E + X) * fscale -> pieces f0 (integer grid) + f1 in the A operand
 // of MMA2, and the 16-term sums of the block's zero-state end state.  FIRST0: block 0 of tile 0, whose rows 0..14 are the
 // carried y history (they do not drive the biquad) and whose row 15 is frame 0.
 template <bool FIRST0>
@@ -555,7 +556,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             }
             w_w += (PROF ? clk() : 0ll) - c2;
         }
-        if (vmax > 60000.f) atomicExch(p.err_flag, 2);
+        // x0 must stay on the integer grid the fp16 piece represents exactly (|g x| <= 1): beyond it the split would be silently
+        // inexact, so the chain reports an error instead
+        if (vmax > 2048.5f) atomicExch(p.err_flag, 2);
         if (PROF && p.prof && warp == 2 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
             pr[kProfCvtWaitRaw] = w_r;
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     } else if (warp < 18) {
         // ================================ FIR drain warps =============================
         // Two warps per TMEM lane quadrant e (channels cg*128 + 32e + lane): role A (warps 10-13) takes the even
-        // blocks of 16 columns, role B (warps 14-17) the odd ones.  Per block: f*2^10 = (E + X) * fscale -> fp16 pieces
+        // blocks of 16 columns, role B (warps 14-17) the odd ones.  Per block: f*2^11 = (E + X) * fscale -> fp16 pieces
         // f0 (integer grid) + f1 into the A operand of MMA2, and the zero-state end state of the block Z_b (16-term float
         // sums) into the TMEM mailbox.  Role A then runs the block-state recursion in double and the look-back.
         const int e = warp & 3;
@@ -639,15 +642,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int b = 0; b < kTcBlocks; b++) {
+                    // the whole block recursion runs in balanced coordinates w = W s (W = S V^T of the block's free-response
+                    // matrix): in the TDF-II basis a filter with poles near z = 1 has free responses that cancel to 1e-2 of
+                    // their terms, which neither the float sums Z_b nor the float states can afford (measured 6e-6 on a 200 Hz
+                    // high-pass)
                     szs[b][0] = d2f_bits(s1);
                     szs[b][1] = d2f_bits(s2);
                     const double n1 = fma(p.A16[0], s1, fma(p.A16[1], s2, f2d_bits(__uint_as_float(z[b][0]))));
                     const double n2 = fma(p.A16[2], s1, fma(p.A16[3], s2, f2d_bits(__uint_as_float(z[b][1]))));
                     s1 = n1;
                     s2 = n2;
-                    if (b == kTcBlocks - 2) {
-                        s10_1 = s1;
-                        s10_2 = s2;
+                    if (b == kTcBlocks - 2) {  // back to the TDF-II basis, which the look-back arrays and K1 use
+                        s10_1 = fma(p.Wbi[0], s1, p.Wbi[1] * s2);
+                        s10_2 = fma(p.Wbi[2], s1, p.Wbi[3] * s2);
                     }
                 }
             }
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             }
             // ---- true state at the start of every block = zero-state part + response to the incoming state -> output warps
             {
-                const float qf0 = d2f_bits(q1), qf1 = d2f_bits(q2);
+                const float qf0 = d2f_bits(fma(p.Wb[0], q1, p.Wb[1] * q2)), qf1 = d2f_bits(fma(p.Wb[2], q1, p.Wb[3] * q2));
                 const int fi = first ? 1 : 0;
                 if (it > 0) mbar_wait(&mbox_free[e], par ^ 1);  // the output warps have read the previous tile's block states
                 asm volatile("tcgen05.fence::after_thread_sync;");
@@ -740,7 +747,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
             } else {
                 // carried biquad state (after row 174) and carried y history (rows 160..174): the only place where the
-                // recursion runs row by row, from the pieces of f just written (f * 2^10 = f0 + f1)
+                // recursion runs row by row, from the pieces of f just written (f * 2^11 = f0 + f1)
                 const double nb1 = p.b1, nb2 = p.b2, na1 = -p.a1, na2 = -p.a2;
                 for (int r = 0; r < kTcHr; r++) {
                     const unsigned char *d = stp + ((kTcBlocks - 1) % kTcRing) * kChunkBytes + (r >> 3) * kKbStride + (r & 7) * 16;
