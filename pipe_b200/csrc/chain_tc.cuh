@@ -196,6 +196,34 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 // Named barrier over the 4 warps of a role group.  Only the group's first warp sleeps on an mbarrier; the others wait here,
 // which costs no issue slots (every mbarrier arrival wakes the warps parked on the CTA's mbarriers).
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// Packed FP32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100): the kernel is bound by instruction issue, and these halve the FP32
+// arithmetic instructions of the converter, the drain and the output warps.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 // One lane of a converged warp.  The tcgen05 / TMA instructions take their operands from uniform registers: issued under
 // `if (lane == 0)` (divergent code) every one of them is wrapped in an ELECT / BRA.U.ANY waterfall with R2UR moves, which cost
 // the single issuing thread ~100 cycles per MMA (measured).  With the whole warp running the control flow and only the issue
@@ -268,7 +296,7 @@ constexpr int kStageBytes = kTcRing * kChunkBytes;              // 73728
 constexpr int kOffZx = kOffStage + kStageBytes;                 // [11][2][128] float: zero-state end state Z_b of every block
 constexpr int kOffBar = kOffZx + kTcBlocks * 2 * kTcCh * 4;
 constexpr int kNumBlkBars = kTcChunks - kTcFirstDone;           // 10: one per chunk 17..26
-constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + kTcBlocks + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 4 + 2;
+constexpr int kNumBars = 2 * kRawStages + 2 * kCvtStages + kNumBlkBars + kTcBlocks + kTcBlocks + 1 + 2 + 2 + 4 + 4 + 4 + 2;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16;
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
@@ -293,24 +321,42 @@ __device__ __forceinline__ void ep_block(const uint32_t (&re)[16], const uint32_
                                          const float *yh, float &p0, float &p1, float &vmax)
 {
     using namespace tc;
+    f32x2 z0 = pk2(0.f, 0.f), z1 = z0;  // even / odd rows of the two block sums
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        float t = __uint_as_float(re[i]) + __uint_as_float(rx[i]), sc = p.fscale;
+    for (int i = 0; i < 16; i += 2) {
+        f32x2 t2 = add2(pk2(__uint_as_float(re[i]), __uint_as_float(re[i + 1])), pk2(__uint_as_float(rx[i]), __uint_as_float(rx[i + 1])));
+        f32x2 sc2 = pk2(p.fscale, p.fscale);
         if (FIRST0 && i < kTcHr) {
-            t = yh[(size_t)i * p.C];
-            sc = p.yh_scale;
+            // rows 0..14 of tile 0 are the carried y history (row 15, in the last pair, is frame 0)
+            float ta, tb;
+            upk2(t2, ta, tb);
+            t2 = pk2(yh[(size_t)i * p.C], i + 1 < kTcHr ? yh[(size_t)(i + 1) * p.C] : tb);
+            sc2 = pk2(p.yh_scale, i + 1 < kTcHr ? p.yh_scale : p.fscale);
         }
-        const float ra = fmaf(t, sc, 12582912.f) - 12582912.f;  // t * sc to the nearest integer (|.| < 2^22)
-        const __half h0 = __float2half_rn(ra);                   // above 2048 the fp16 grid is coarser than 1:
-        const __half h1 = __float2half_rn(fmaf(t, sc, -__half2float(h0)));  // the remainder is taken from what h0 really holds
-        vmax = fmaxf(vmax, fabsf(ra));
-        if (!FIRST0 || i >= kTcHr) {  // Wz is pre-multiplied by fscale
-            p0 = fmaf(p.Wz[i][0], t, p0);
-            p1 = fmaf(p.Wz[i][1], t, p1);
-        }
-        *reinterpret_cast<__half *>(dst + (i >> 3) * kKbStride + (i & 7) * 16) = h0;
-        *reinterpret_cast<__half *>(dst + (i >> 3) * kKbStride + (i & 7) * 16 + kPieceBytes) = h1;
+        float ra, rb;  // t * sc to the nearest integer (|.| < 2^22)
+        upk2(add2(fma2(t2, sc2, pk2(12582912.f, 12582912.f)), pk2(-12582912.f, -12582912.f)), ra, rb);
+        const __half2 h0 = __floats2half2_rn(ra, rb);  // above 2048 the fp16 grid is coarser than 1:
+        const float2 f0 = __half22float2(h0);           // the remainder is taken from what h0 really holds
+        float la, lb;
+        upk2(fma2(t2, sc2, pk2(-f0.x, -f0.y)), la, lb);
+        const __half2 h1 = __floats2half2_rn(la, lb);
+        vmax = fmaxf(vmax, fmaxf(fabsf(ra), fabsf(rb)));
+        // Wz is pre-multiplied by fscale; the history rows of tile 0 do not drive the biquad
+        const float w0a = (FIRST0 && i < kTcHr) ? 0.f : p.Wz[i][0], w1a = (FIRST0 && i < kTcHr) ? 0.f : p.Wz[i][1];
+        const float w0b = (FIRST0 && i + 1 < kTcHr) ? 0.f : p.Wz[i + 1][0], w1b = (FIRST0 && i + 1 < kTcHr) ? 0.f : p.Wz[i + 1][1];
+        z0 = fma2(pk2(w0a, w0b), t2, z0);
+        z1 = fma2(pk2(w1a, w1b), t2, z1);
+        unsigned char *d = dst + (i >> 3) * kKbStride + (i & 7) * 16;
+        *reinterpret_cast<__half *>(d) = __low2half(h0);
+        *reinterpret_cast<__half *>(d + 16) = __high2half(h0);
+        *reinterpret_cast<__half *>(d + kPieceBytes) = __low2half(h1);
+        *reinterpret_cast<__half *>(d + 16 + kPieceBytes) = __high2half(h1);
     }
+    float a, b;
+    upk2(z0, a, b);
+    p0 += a + b;
+    upk2(z1, a, b);
+    p1 += a + b;
 }
 
 // PROF: per-role cycle counters (PB_TC_PROF=1); a compile-time switch, the counters cost the single-warp issue loops dearly
@@ -333,8 +379,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     uint64_t *stage_free = a2_ready + kTcBlocks;    //      MMA2 (commit) -> drain: the staging tile has been consumed
     uint64_t *d2_full = stage_free + 1;             // [2]  MMA2 (commit) -> output warps
     uint64_t *d2_empty = d2_full + 2;               // [2]  output warps -> MMA2
-    uint64_t *state_ready = d2_empty + 2;           // [4]  drain warp e -> output warp e: incoming state in sstate
-    uint64_t *mbox_ready = state_ready + 4;         // [4]  drain warp e -> output warp e: block states in the TMEM mailbox
+    uint64_t *mbox_ready = d2_empty + 2;            // [4]  drain warps A (all four arrive on [0]) -> output warps: block states in the TMEM mailbox
     uint64_t *mbox_free = mbox_ready + 4;           // [4]  output warp e -> drain warps e
     uint64_t *zx_ready = mbox_free + 4;             // [4]  drain warp B -> drain warp A: the Z of the odd blocks are in D1's dead columns
     uint64_t *slice_done = zx_ready + 4;            // [2]  MMA2 (commit) -> drain: slices 0 / 1 have read ring slots 0,1 / 2
@@ -366,8 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&d2_empty[i], 1);
         }
         for (int i = 0; i < 4; i++) {
-            mbar_init(&state_ready[i], 1);
-            mbar_init(&mbox_ready[i], 1);
+            mbar_init(&mbox_ready[i], 4);  // only [0] is used: all four quadrants arrive, one output warp waits
             mbar_init(&mbox_free[i], 2);
             mbar_init(&zx_ready[i], 1);
             if (i < 2) mbar_init(&slice_done[i], 1);
@@ -530,10 +574,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     // x * scale rounded to the nearest integer on the FMA pipe (|.| < 2^22; larger values trip the range check),
-                    // and the remainder with a single rounding
-                    const float ra = fmaf(v[2 * i], sc, 12582912.f) - 12582912.f, rb = fmaf(v[2 * i + 1], sc, 12582912.f) - 12582912.f;
+                    // and the remainder with a single rounding; two values per instruction
+                    const f32x2 x2 = pk2(v[2 * i], v[2 * i + 1]), s2 = pk2(sc, sc);
+                    const f32x2 r2 = add2(fma2(x2, s2, pk2(12582912.f, 12582912.f)), pk2(-12582912.f, -12582912.f));
+                    float ra, rb, la, lb;
+                    upk2(r2, ra, rb);
+                    upk2(fma2(x2, s2, pk2(-ra, -rb)), la, lb);
                     hi[i] = __floats2half2_rn(ra, rb);
-                    lo[i] = __floats2half2_rn(fmaf(v[2 * i], sc, -ra), fmaf(v[2 * i + 1], sc, -rb));
+                    lo[i] = __floats2half2_rn(la, lb);
                     vmax = fmaxf(vmax, fmaxf(fabsf(ra), fabsf(rb)));
                 }
                 const int off = (1 - kb) * 2048 + mb * 128 + fr_i * 16;  // K-blocks swapped (Toeplitz trick)
@@ -614,7 +662,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 group_sync(gid);
                 if (gl && lane == 0) {
                     mbar_arrive(&a2_ready[b]);
-                    mbar_arrive(&d1_free[b]);  // all four quadrants have read the block's columns
+                    // all four quadrants have read the block's columns.  The last block is released only after role A has
+                    // read the block sums below: that keeps the next tile's role B (which overwrites them) behind MMA1 chunk 10
+                    if (b != kTcBlocks - 1) mbar_arrive(&d1_free[b]);
                 }
                 zx[(2 * b + 0) * kTcCh + e * 32 + lane] = p0;
                 zx[(2 * b + 1) * kTcCh + e * 32 + lane] = p1;
@@ -639,6 +689,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     z[b][0] = __float_as_uint(zx[(2 * b + 0) * kTcCh + e * 32 + lane]);
                     z[b][1] = __float_as_uint(zx[(2 * b + 1) * kTcCh + e * 32 + lane]);
                 }
+                group_sync(gid);
+                if (gl && lane == 0) mbar_arrive(&d1_free[kTcBlocks - 1]);
                 double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int b = 0; b < kTcBlocks; b++) {
@@ -733,7 +785,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&mbox_ready[e]);
+                if (lane == 0) mbar_arrive(&mbox_ready[0]);
             }
             // true state after row 159
             double I0 = q1, I1 = q2;
@@ -794,11 +846,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             for (int s = 0; s < kRsSlices; s++, nsl++) {
                 const uint32_t b = nsl & 1u;
                 const long long k6 = (PROF ? clk() : 0ll);
-                if (warp == 18) mbar_wait(&d2_full[b], (nsl >> 1) & 1u);
+                if (warp == 18) {
+                    mbar_wait(&d2_full[b], (nsl >> 1) & 1u);
+                    if (s == 0) mbar_wait(&mbox_ready[0], par);  // the block states of all four quadrants are in the mailbox
+                }
                 const long long g0 = (PROF ? clk() : 0ll);
                 asm volatile("bar.sync 5, 256;" ::: "memory");
                 o_sync += (PROF ? clk() : 0ll) - g0;
-                if (s == 0) mbar_wait(&mbox_ready[e], par);
                 const long long k7 = (PROF ? clk() : 0ll);
                 r_w += k7 - k6;
                 asm volatile("tcgen05.fence::after_thread_sync;");
@@ -814,9 +868,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 if (s == kRsSlices - 1 && lane == 0) mbar_arrive(&mbox_free[e]);
                 const long long k9 = (PROF ? clk() : 0ll);
                 o_ld += k9 - k7;
-                float sb[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) sb[k] = __uint_as_float(zs[k]);
+                const f32x2 sb01 = pk2(__uint_as_float(zs[0]), __uint_as_float(zs[1])), sb23 = pk2(__uint_as_float(zs[2]), __uint_as_float(zs[3]));
+                const f32x2 sb45 = pk2(__uint_as_float(zs[4]), __uint_as_float(zs[5])), sb67 = pk2(__uint_as_float(zs[6]), __uint_as_float(zs[7]));
                 const int nout = ((s == kRsSlices - 1) ? kTcOut - kRsN * (kRsSlices - 1) : kRsN) - 16 * hsel;
                 const unsigned char *rcg = stage + ((((first && s == 0) ? kTcRcFirst : kRsN * s) >> 3) + 2 * hsel) * kKbStride + 128;
                 float *op = outp + (size_t)(kRsN * s + 16 * hsel) * p.C;
@@ -825,9 +878,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     const unsigned char *rci = rcg + (i >> 3) * kKbStride + 2 * (i & 7) * kMbStride;
                     const float4 ca = *reinterpret_cast<const float4 *>(rci);
                     const float4 cb = *reinterpret_cast<const float4 *>(rci + kMbStride);
-                    const float c0 = fmaf(ca.y, sb[1], ca.x * sb[0]), c1 = fmaf(ca.w, sb[3], ca.z * sb[2]);
-                    const float c2 = fmaf(cb.y, sb[5], cb.x * sb[4]), c3 = fmaf(cb.w, sb[7], cb.z * sb[6]);
-                    const float o = fmaf(__uint_as_float(e16[i]) + __uint_as_float(x16[i]), p.descale_rs, (c0 + c1) + (c2 + c3));
+                    f32x2 acc = mul2(pk2(ca.x, ca.y), sb01);
+                    acc = fma2(pk2(ca.z, ca.w), sb23, acc);
+                    acc = fma2(pk2(cb.x, cb.y), sb45, acc);
+                    acc = fma2(pk2(cb.z, cb.w), sb67, acc);
+                    float c0, c1;
+                    upk2(acc, c0, c1);
+                    const float o = fmaf(__uint_as_float(e16[i]) + __uint_as_float(x16[i]), p.descale_rs, c0 + c1);
                     if (i < nout) {
                         op[(size_t)i * p.C] = o;
                         if (meter) {
