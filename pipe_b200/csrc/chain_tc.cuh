@@ -27,10 +27,12 @@
 //   x*2^11 = x0 + x1,  h*2^sh = h0 + h1 + h2,  x0 and h0 integer-valued fp16 (|.| <= 2048), the others
 //   fp16 remainders (h needs the third piece: the remainder of a tap has ABSOLUTE precision 2^-13 of the
 //   grid, which summed over 257 taps was 5.7e-7 of the peak).  x0*h0 goes to accumulator E: every product
-//   and every partial sum is an integer below 2^24, so E is EXACT.  x0*h1 + x0*h2 + x1*h0 + x1*h1 go to
-//   accumulator X, 2^-9 of E in magnitude, whose truncation is negligible.  Modelled FIR error 6e-8.
+//   and every partial sum is an integer below 2^24, so E is EXACT.  x0*h1 + x0*h2 + x1*h go to
+//   accumulator X, 2^-9 of E in magnitude, whose truncation is negligible (x1 is multiplied by the tap rounded once:
+//   four passes).  Modelled FIR error 1.3e-7.
 //   MMA2 uses the same scheme with two pieces each (f*2^11 = f0 + f1, P*2^sh2 = p0 + p1; at most 32 rows per
-//   output): E2 = f0*p0 exact, X2 = f0*p1 + f1*p0 + f1*p1.  Modelled error 2.2e-7 of the peak.
+//   output): E2 = f0*p0 exact, X2 = f0*p1 + f1*p0 + f1*p1.  Modelled error 2.2e-7 of the peak.  The grids are FIXED, so
+//   the noise floor is 2^-24 of full scale (|g x| = 1), not of each channel's own level.
 //
 // B operand of MMA1: the Toeplitz matrix is never materialised.  A K-major 8x8 core matrix depends only on
 // (column block - row block); with the two K-blocks of an instruction stored swapped in A, the
@@ -38,12 +40,16 @@
 // positions.  B operand of MMA2: the 19 blocks [32 outputs x 16 rows] of P, 1 KB per piece, the two pieces
 // adjacent so that one N = 64 instruction multiplies f0 by [p0 | p1] into [E2 | X2].
 //
-// Roles (608 threads): warp 0 TMA producer, warp 1 MMA1 issuer, warps 2-5 / 6-9 two converter groups on
-// alternate chunks (f32 tile -> x0/x1 in the MN-major UMMA layout), warps 10-13 FIR drain (one per TMEM lane
-// quadrant: D1 -> f pieces in the MN-major UMMA layout for MMA2, 16 columns at a time as MMA1's last chunks
-// complete them; block states, look-back), warps 14-17 output (per slice: D2 -> registers, block-state
-// correction, coalesced stores, meter), warp 18 MMA2 issuer.  Tiles follow a static time-major schedule over a
-// persistent grid.  The drain warps hand the 11 block states to the output warps through 24 spare TMEM columns.
+// Roles (864 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA1 issuer, warps 2-5 / 6-9 two converter
+// groups on alternate chunks (f32 tile -> x0/x1 in the MN-major UMMA layout), warps 10-13 / 14-17 two FIR drain groups on
+// the even / odd 16-column blocks of D1 (one warp per TMEM lane quadrant in each: D1 -> f pieces in the MN-major UMMA
+// layout for MMA2, block by block as MMA1's last chunks complete them; the first group then runs the block-state recursion
+// and the look-back), warps 18-21 / 22-25 two output groups on the two halves of every slice (D2 -> registers, free the
+// buffer, block-state correction, coalesced stores, meter), warp 26 MMA2 issuer.  Tiles follow a static time-major schedule.
+// The drain warps hand the 11 block states to the output warps through 24 spare TMEM columns.  Inside a role group only the
+// first warp polls mbarriers, the others wait on a named barrier; the issuing warps run converged and elect one lane per
+// tcgen05 instruction.  MMA1 writes the first touch of every 16 columns with accumulate = 0 and waits for the previous
+// tile's drain per column block, so it overlaps the tail of that drain.
 #pragma once
 
 #include <cuda.h>
