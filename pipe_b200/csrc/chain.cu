@@ -478,11 +478,11 @@ static bool tc_shape_ok(const pb_chain *c, const Segment &s)
 static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_t n, void *out, bool is_last_segment,
                                  cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // function attributes are per device
+    if (c->device < 0 || c->device >= 64 || !attr_set[c->device]) {
         PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        attr_set = true;
+        if (c->device >= 0 && c->device < 64) attr_set[c->device] = true;
     }
     TcParams p{};
     int32_t r = make_frame_map(&p.tm_in, in, c->C, n);
