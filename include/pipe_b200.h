@@ -90,6 +90,7 @@ typedef struct pb_chain_desc {
 
 #define PB_CHAIN_METER 1u       /* fused meter sink: per-channel peak and sum of squares of the output */
 #define PB_CHAIN_NO_TENSOR 2u   /* never take the tcgen05 FIR path */
+#define PB_CHAIN_NO_STREAM 4u   /* never take the streaming kernels: the generic tile kernel serves FIR-less runs too */
 
 typedef struct pb_chain pb_chain;
 
@@ -144,7 +145,8 @@ int32_t pb_chain_set_stage(pb_chain *c, int32_t stage_index, const pb_stage_desc
 int32_t pb_chain_meter_read(pb_chain *c, double *peak, double *sumsq, int64_t *frames);
 
 /* Which kernel family served the last process call: 0 none yet, 1 generic
- * fused tile kernel, 2 tcgen05/TMA chain kernel.  kernels = launches so far. */
+ * fused tile kernel, 2 tcgen05/TMA chain kernel, 3 streaming kernels (runs without
+ * FIR and resampler).  kernels = launches so far. */
 int32_t pb_chain_last_path(const pb_chain *c, int32_t *path, int64_t *kernel_launches);
 
 /* ---- Source / Sink side kernels ----------------------------------------- */

@@ -20,7 +20,7 @@ PB_ERR_INVALID, PB_ERR_CUDA, PB_ERR_NO_DEVICE, PB_ERR_NOMEM = -1, -2, -3, -4
 PB_ERR_UNSUPPORTED, PB_ERR_CAPACITY, PB_ERR_STATE = -5, -6, -7
 PB_F32, PB_F64 = 0, 1
 STAGE_COPY, STAGE_GAIN, STAGE_BIQUAD, STAGE_FIR, STAGE_RESAMPLE = range(5)
-CHAIN_METER, CHAIN_NO_TENSOR = 1, 2
+CHAIN_METER, CHAIN_NO_TENSOR, CHAIN_NO_STREAM = 1, 2, 4
 
 _KINDS = {"copy": 0, "gain": 1, "biquad": 2, "fir": 3, "resample": 4}
 _ERR_NAMES = {-1: "PB_ERR_INVALID", -2: "PB_ERR_CUDA", -3: "PB_ERR_NO_DEVICE", -4: "PB_ERR_NOMEM",

@@ -11,6 +11,7 @@
 #include <new>
 #include <vector>
 
+#include "chain_stream.cuh"
 #include "chain_tc.cuh"
 #include "chain_tile.cuh"
 
@@ -55,6 +56,11 @@ struct Segment {
     double tc_Wb[4], tc_Wbi[4];
     bool tc_level_ok = true;                         // the biquad keeps the broadband level (see build_tc_tables)
     std::vector<float> tc_rc;                        // [147 + 32][8] output correction per block state (see chain_tc.cuh)
+    // K3 (streaming kernels): runs without FIR and without resampler
+    bool st_ok = false;
+    int st_grid = 0;
+    void *d_st_tab = nullptr;                        // StTab
+    double st_wt[32][2] = {};                        // A^k B, passed in the kernel parameters
 };
 
 struct Slot {  // one in-flight batch of the pipelined host path
@@ -168,7 +174,7 @@ static void plan_segments(pb_chain *c)
 static void free_segment(Segment &s)
 {
     void *ptrs[] = {s.d_taps, s.d_wt, s.d_apow, s.d_coef, s.d_xhist[0], s.d_xhist[1], s.d_yhist[0], s.d_yhist[1],
-                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables, s.d_tc_rc};
+                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables, s.d_tc_rc, s.d_st_tab};
     for (void *p : ptrs)
         if (p) cudaFree(p);
 }
@@ -611,6 +617,39 @@ static int32_t refresh_segment_params(pb_chain *c, Segment &s)
         }
         PB_CUDA(upload<double>(s.d_apow, apow));
         PB_CUDA(upload<double>(s.d_wt, wt));
+        if (s.st_ok) {
+            // K3 tables (chain_stream.cuh), R rows per warp: A^k B for k < R (kernel parameters), A^(R j) for j <= 16,
+            // (A^T)^i for i <= 32 and (A^T)^(32 w) for w < 16 with the tile step T = 16 R
+            const int R = c->dtype == PB_F32 ? StShape<float>::kRows : StShape<double>::kRows;
+            std::vector<double> tab((size_t)StTab::kCount);
+            auto mul = [](const double *X, const double *Y, double *Z) {
+                const double r[4] = {X[0] * Y[0] + X[1] * Y[2], X[0] * Y[1] + X[1] * Y[3], X[2] * Y[0] + X[3] * Y[2], X[2] * Y[1] + X[3] * Y[3]};
+                for (int i = 0; i < 4; i++) Z[i] = r[i];
+            };
+            double P[4] = {1, 0, 0, 1};
+            for (int k = 0; k <= kStWarps * R; k++) {
+                if (k < R) {
+                    s.st_wt[k][0] = P[0] * B[0] + P[1] * B[1];
+                    s.st_wt[k][1] = P[2] * B[0] + P[3] * B[1];
+                }
+                if (k % R == 0)
+                    for (int i = 0; i < 4; i++) tab[StTab::kPw + 4 * (k / R) + i] = P[i];
+                mul(P, A, P);
+            }
+            const double *AT = &tab[StTab::kPw + 4 * kStWarps];  // A^T
+            double Q[4] = {1, 0, 0, 1};
+            for (int i = 0; i <= kStWin; i++) {
+                for (int e = 0; e < 4; e++) tab[StTab::kLb + 4 * i + e] = Q[e];
+                mul(Q, AT, Q);
+            }
+            const double *A32 = &tab[StTab::kLb + 4 * kStWin];   // (A^T)^32
+            double W[4] = {1, 0, 0, 1};
+            for (int w = 0; w < kStWarps; w++) {
+                for (int e = 0; e < 4; e++) tab[StTab::kMw + 4 * w + e] = W[e];
+                mul(W, A32, W);
+            }
+            PB_CUDA(upload<double>(s.d_st_tab, tab));
+        }
     }
     if (s.rs_stage >= 0) {
         const auto &st = c->stages[s.rs_stage];
@@ -637,6 +676,7 @@ static int32_t build_segment(pb_chain *c, Segment &s)
         s.Hr = s.P - 1;
     }
     const bool has_fir = s.fir_stage >= 0;
+    s.st_ok = !has_fir && s.rs_stage < 0 && !(c->flags & PB_CHAIN_NO_STREAM);
     // tile length
     auto smem_for = [&](int L) {
         const int tp_len = has_fir ? (s.Hf + 1) + 2 * s.FB + s.FB : 0;
@@ -667,12 +707,20 @@ static int32_t build_segment(pb_chain *c, Segment &s)
         int32_t r = configure_kernel<double, 8>(c, s);
         if (r != PB_OK) return r;
     }
+    if (s.st_ok) {
+        int per_sm = 0;
+        if (f32) PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<float>, kStThreads, 0));
+        else PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<double>, kStThreads, 0));
+        if (per_sm < 1) return fail(PB_ERR_UNSUPPORTED, "streaming kernel does not fit on an SM");
+        s.st_grid = per_sm * c->num_sms;
+    }
     // tables
     if (has_fir) PB_CUDA(cudaMalloc(&s.d_taps, el * (size_t)s.tp_len));
     if (s.bq_stage >= 0) {
         PB_CUDA(cudaMalloc(&s.d_apow, sizeof(double) * (size_t)s.apow_len * 4));
         PB_CUDA(cudaMalloc(&s.d_wt, sizeof(double) * (size_t)s.wt_len * 2));
-        s.lb_tiles = (int)ceil_div64(c->max_frames, std::min(s.L, kTcFrames)) + 1;
+        s.lb_tiles = (int)ceil_div64(c->max_frames, std::min(s.L, s.st_ok ? kStMinTile : kTcFrames)) + 1;
+        if (s.st_ok) PB_CUDA(cudaMalloc(&s.d_st_tab, sizeof(double) * (size_t)StTab::kCount));
         const size_t groups = (size_t)(c->C + kCg - 1) / kCg;
         PB_CUDA(cudaMalloc(&s.d_agg, sizeof(double) * groups * s.lb_tiles * 64));
         PB_CUDA(cudaMalloc(&s.d_inc, sizeof(double) * groups * s.lb_tiles * 64));
@@ -775,6 +823,60 @@ static int32_t launch_segment(pb_chain *c, Segment &s, const void *in, int64_t n
     return PB_OK;
 }
 
+// K3: one launch of the streaming kernels (chain_stream.cuh) for a run without FIR and without resampler.
+template <typename T, typename V>
+static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, int64_t n, void *out, bool is_last_segment,
+                                     cudaStream_t stream)
+{
+    const bool has_bq = s.bq_stage >= 0;
+    const bool meter = is_last_segment && (c->flags & PB_CHAIN_METER);
+    // same gain folding as K1: everything in front of the biquad is applied at load in T, everything behind it to the double result
+    const double g_front = s.g[0] * s.g[1], g_back = s.g[2] * s.g[3];
+    if (!has_bq && !meter && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+        const int64_t nvals = n * c->C;
+        const int64_t per_cta = 256 * 4 * (int64_t)(16 / sizeof(T));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nvals, per_cta), (int64_t)c->num_sms * 8));
+        stream_map_kernel<T, V><<<grid, 256, 0, stream>>>((const T *)in, (T *)out, nvals, (T)(g_front * g_back));
+        PB_CUDA(cudaGetLastError());
+        c->launches++;
+        return PB_OK;
+    }
+    StreamParams<T> p{};
+    p.in = (const T *)in;
+    p.out = (T *)out;
+    p.n_frames = n;
+    p.C = c->C;
+    p.n_tiles = (int)ceil_div64(n, StShape<T>::kTile);
+    p.n_groups = (c->C + kCg - 1) / kCg;
+    p.has_bq = has_bq;
+    p.g_load = has_bq ? (T)g_front : (T)(g_front * g_back);
+    p.g_bq = has_bq ? g_back : 1.0;
+    p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
+    memcpy(p.wt, s.st_wt, sizeof(p.wt));
+    p.tab = (const double *)s.d_st_tab;
+    p.bq_state = (const double *)s.d_state[s.pp];
+    p.bq_state_next = (double *)s.d_state[s.pp ^ 1];
+    p.lb_agg = (double *)s.d_agg;
+    p.lb_inc = (double *)s.d_inc;
+    p.lb_status = s.d_status;
+    c->epoch = (c->epoch % 0x3ffffffeu) + 1u;
+    p.epoch = c->epoch;
+    p.meter_peak = meter ? c->d_meter : nullptr;
+    p.meter_sumsq = meter ? c->d_meter + c->C : nullptr;
+    p.ticket = c->d_ticket;
+    p.ticket_base = c->ticket_base;
+    p.err_flag = reinterpret_cast<int *>(c->d_ticket + 1);
+    if (has_bq && p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
+    const int64_t total = (int64_t)p.n_tiles * p.n_groups;
+    const int grid = (int)std::min<int64_t>(total, s.st_grid);
+    chain_stream_kernel<T><<<grid, kStThreads, 0, stream>>>(p);
+    PB_CUDA(cudaGetLastError());
+    c->ticket_base += (unsigned long long)total + (unsigned long long)grid;
+    c->launches++;
+    if (has_bq) s.pp ^= 1;
+    return PB_OK;
+}
+
 // per-buffer output frame counts through every resampling segment (integer bookkeeping)
 static void count_outputs(pb_chain *c, const int64_t *buf_frames, int n_buffers, int64_t *buf_out, int64_t *total_in,
                           int64_t *total_out, bool commit)
@@ -828,11 +930,13 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
             // K2 needs the call aligned to 160-frame tiles (then the resampler phase is 0 at every tile start)
             const bool use_tc = s.tc_ok && s.acc == 0 && n >= kTcFrames && n % kTcFrames == 0 && s.g[2] != 0.0 && s.tc_level_ok &&
                                 ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
-            int32_t r = use_tc ? launch_segment_tc(c, s, src, n, dst, lastseg, stream)
+            int32_t r = use_tc       ? launch_segment_tc(c, s, src, n, dst, lastseg, stream)
+                        : s.st_ok    ? (c->dtype == PB_F32 ? launch_segment_stream<float, float4>(c, s, src, n, dst, lastseg, stream)
+                                                           : launch_segment_stream<double, double2>(c, s, src, n, dst, lastseg, stream))
                         : c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, src, n, dst, lastseg, stream)
                                              : launch_segment<double, 8>(c, s, src, n, dst, lastseg, stream);
             if (r != PB_OK) return r;
-            path = std::max(path, use_tc ? 2 : 1);
+            path = std::max(path, use_tc ? 2 : s.st_ok ? 3 : 1);
             if (s.rs_stage >= 0) n = (s.acc + n * s.up) / s.down;  // s.acc is committed below, after every launch used it
             src = dst;
             if (n == 0 && !lastseg) {

@@ -1,0 +1,409 @@
+// chain_stream.cuh -- K3, the streaming kernels for Processor runs without FIR and without resampler:
+//     [gain* | copy] [biquad]? [gain*]
+// i.e. BASELINE.json configs[0] (mock.Processor copy, reference mock/mock.go:147-154) and configs[1] (gain + biquad).
+// Like K1 they replace the ProcessFunc walk of Processor.execute (reference pipe.go:425-451, the call at :438) for the
+// run; unlike K1 these runs are HBM-bound (8 B per f32 sample, 16 B per f64 sample), so the kernels are built around
+// bytes in flight and instructions per row instead of shared-memory tiles:
+//
+//   stream_map_kernel     out = g * in over the flat buffer (copy / gain-only runs without meter): 16 B vectors,
+//                         four independent loads per thread before the first store, streaming cache hints.
+//   chain_stream_kernel   gain + biquad (+ fused meter sink).  A tile is 32 channels x 8 R frames (R = 32 for f32, 16 for
+//                         f64: 32 KB in, 32 KB out); each of the 8 warps holds its R rows IN REGISTERS (one coalesced
+//                         128 B / 256 B row per load instruction, nothing staged in shared memory), so one HBM read and one
+//                         HBM write per sample is all the traffic there is.  The biquad (TDF-II, double, the same carried
+//                         state [C][2] as K1/K2) is parallelised in time as in K1: zero-state end state of every R-row
+//                         sub-chunk (2 independent DFMA per sample), tile aggregate, decoupled look-back across tiles, the
+//                         true recursion from the resolved state (5 DFMA per sample).  What differs from K1, because the
+//                         look-back latency is what bounds an HBM-bound tile kernel (measured: 60-80 % of a tile's time
+//                         with one warp walking predecessors while the others wait at a barrier):
+//                           * sub-chunk prefix states are computed by every warp in parallel from a table of A^(R j);
+//                           * ALL 8 warps look back, warp w over the window of 32 predecessors [32 w, 32 w + 32): each
+//                             folds its window (independent FMAs against a table of (A^T)^i) and the partial results are
+//                             combined up to the first window that held an inclusive state.  A tile therefore never waits
+//                             for an inclusive state to appear, only for aggregates, which depend on nothing -- with few
+//                             channel groups (configs[1] has 2) more than a hundred tiles of one group are in flight;
+//                             the last warp keeps sliding if 256 predecessors hold aggregates only;
+//                           * one release per publication and no fence after the acquire (the warp barrier orders the
+//                             lanes): MEMBARs were half of the look-back time;
+//                           * full tiles take a path without per-row predicates, tables with static indices sit in the
+//                             kernel parameters (constant-bank operands of the DFMAs): ~20 instead of ~78 instructions
+//                             per sample.
+#pragma once
+
+#include "chain_tile.cuh"
+
+namespace pb {
+
+constexpr int kStThreads = 256;
+constexpr int kStWarps = kStThreads / 32;        // 8 sub-chunks per tile, and 8 look-back windows
+constexpr int kStWin = 32;                       // look-back window (one predecessor per lane)
+template <typename T>
+struct StShape {
+    static constexpr int kRows = sizeof(T) == 4 ? 32 : 16;   // rows a warp keeps in registers
+    static constexpr int kTile = kStWarps * kRows;            // frames per tile: 256 (f32) / 128 (f64)
+};
+constexpr int kStMinTile = 128;
+
+// double tables in global memory, copied to shared memory at kernel start (dynamic indices)
+struct StTab {
+    static constexpr int kPw = 0;                          // [9][4]   A^(R j), j = 0..8  (j = 8: the tile step A^T)
+    static constexpr int kLb = kPw + 4 * (kStWarps + 1);   // [33][4]  (A^T)^i, i = 0..32
+    static constexpr int kMw = kLb + 4 * (kStWin + 1);     // [8][4]   (A^T)^(32 w), w = 0..7
+    static constexpr int kCount = kMw + 4 * kStWarps;
+};
+
+template <typename T>
+struct StreamParams {
+    const T *in;
+    T *out;
+    int64_t n_frames;
+    int C, n_tiles, n_groups;
+    T g_load;             // gains in front of the biquad (all gains of the run when there is none), applied in T like K1
+    double g_bq;          // gains behind the biquad, applied to the double result before the single rounding to T
+    int has_bq;
+    double b0, b1, b2, a1, a2;
+    double wt[32][2];     // A^k B, k < R: constant-bank operands (static indices after unrolling)
+    const double *tab;    // StTab
+    const double *bq_state;
+    double *bq_state_next;
+    double *lb_agg, *lb_inc;
+    unsigned *lb_status;
+    unsigned epoch;
+    double *meter_peak, *meter_sumsq;
+    unsigned long long *ticket;
+    unsigned long long ticket_base;
+    int *err_flag;
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void mat2_fma(const double *__restrict__ m, double v0, double v1, double &a0, double &a1)
+{
+    a0 = fma(m[0], v0, fma(m[1], v1, a0));
+    a1 = fma(m[2], v0, fma(m[3], v1, a1));
+}
+
+// f32 -> f64 for pass 2.  The rows are converted once per pass ON PURPOSE: written as a plain cast the compiler merges the two
+// conversions of a row and keeps 32 doubles (64 registers) alive across the look-back, which spills half of the tile.
+__device__ __forceinline__ double to_double_again(float v)
+{
+    double d;
+    asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(v));
+    return d;
+}
+__device__ __forceinline__ double to_double_again(double v) { return v; }
+
+// One look-back window: lane i watches tile base - i of group status array st_g.  Returns the position of the first
+// inclusive state (0..31), 32 when the window holds aggregates only, -1 on timeout.  Lanes before the stream start
+// (base - i < 0) count as inclusive; they never come first because tile 0 publishes an inclusive state.
+__device__ __forceinline__ int st_poll_window(const unsigned *st_g, int base, int lane, unsigned epoch, int *err_flag)
+{
+    const int j = base - lane;
+    for (unsigned spins = 0;; spins++) {
+        unsigned st = kLbInc;
+        if (j >= 0) {
+            st = ld_acquire_u32(st_g + j);
+            st = ((st >> 2) == epoch) ? (st & 3u) : kLbNone;
+        }
+        const unsigned ready = __ballot_sync(0xffffffffu, st != kLbNone);
+        const unsigned inc = __ballot_sync(0xffffffffu, st == kLbInc);
+        if (inc) {
+            const int first_inc = __ffs(inc) - 1;
+            const unsigned need = (first_inc == 0) ? 0u : (0xffffffffu >> (32 - first_inc));
+            if ((ready & need) == need) return first_inc;
+        } else if (ready == 0xffffffffu) {
+            return kStWin;
+        }
+        if (spins > (1u << 24)) {  // ~1 s: a predecessor never published
+            if (lane == 0) atomicExch(err_flag, 1);
+            return -1;
+        }
+        __nanosleep(32);
+    }
+}
+
+// w += sum_{i < first_inc} (A^T)^i Z_{base-i}  (+ (A^T)^first_inc Inc_{base-first_inc} when first_inc < 32), this lane's channel
+__device__ __forceinline__ void st_fold_window(const double *agg_g, const double *inc_g, const double *lb_s, int base, int first_inc,
+                                               int lane, double &w0, double &w1)
+{
+#pragma unroll 1
+    for (int i0 = 0; i0 < first_inc; i0 += 4) {  // payloads four at a time: one L2 round trip per batch is exposed
+        double2 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = (i0 + u < first_inc) ? i0 + u : first_inc - 1;
+            a[u] = __ldcg(reinterpret_cast<const double2 *>(agg_g + (size_t)(base - i) * 64 + lane * 2));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u < first_inc) mat2_fma(lb_s + 4 * (i0 + u), a[u].x, a[u].y, w0, w1);
+    }
+    if (first_inc < kStWin) {
+        const double2 q = __ldcg(reinterpret_cast<const double2 *>(inc_g + (size_t)(base - first_inc) * 64 + lane * 2));
+        mat2_fma(lb_s + 4 * first_inc, q.x, q.y, w0, w1);
+    }
+}
+
+// 256 predecessors with aggregates only: the last warp keeps sliding window by window (tile 0 ends the walk).  Rare, and kept
+// out of line so that its registers do not count against the kernel's.
+__device__ __noinline__ double2 st_slide(const unsigned *st_g, const double *agg_g, const double *inc_g, const double *lb_s, int base,
+                                         int lane, unsigned epoch, int *err_flag, double w0, double w1)
+{
+    double M[4] = {1.0, 0.0, 0.0, 1.0};  // (A^T)^(32 windows walked)
+    const double *ML = lb_s + 4 * kStWin;
+    for (;;) {
+        base -= kStWin;
+        const double n0 = M[0] * ML[0] + M[1] * ML[2], n1 = M[0] * ML[1] + M[1] * ML[3];
+        const double n2 = M[2] * ML[0] + M[3] * ML[2], n3 = M[2] * ML[1] + M[3] * ML[3];
+        M[0] = n0; M[1] = n1; M[2] = n2; M[3] = n3;
+        const int first_inc = st_poll_window(st_g, base, lane, epoch, err_flag);
+        __syncwarp();
+        double v0 = 0.0, v1 = 0.0;
+        if (first_inc >= 0) st_fold_window(agg_g, inc_g, lb_s, base, first_inc, lane, v0, v1);
+        mat2_fma(M, v0, v1, w0, w1);
+        if (first_inc < kStWin) return make_double2(w0, w1);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __grid_constant__ StreamParams<T> p)
+{
+    constexpr int R = StShape<T>::kRows, kTile = StShape<T>::kTile;
+    __shared__ double tab_s[StTab::kCount];
+    __shared__ double zq_s[kStWarps * kCg * 2];    // zero-state end state of every sub-chunk; reused for the meter partials
+    __shared__ double part_s[kStWarps * kCg * 2];  // look-back partial of every window
+    __shared__ double zsum_s[kCg * 2];             // tile aggregate, parked by warp 0 across the look-back
+    __shared__ int flag_s[kStWarps];               // window w held an inclusive state (the combination stops there)
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C;
+    const int total_tiles = p.n_tiles * p.n_groups;
+    const bool meter = p.meter_peak != nullptr;
+    if (p.has_bq)
+        for (int i = tid; i < StTab::kCount; i += kStThreads) tab_s[i] = p.tab[i];
+    const double *pw_s = tab_s + StTab::kPw, *lb_s = tab_s + StTab::kLb, *mw_s = tab_s + StTab::kMw;
+
+    for (;;) {
+        __syncthreads();  // previous tile done with shared memory (and the tables visible)
+        if (tid == 0) s_tile = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= total_tiles) break;
+        // time-major tickets: a tile only waits on smaller tickets, which resident CTAs already hold
+        const int t = tile / p.n_groups, g = tile - t * p.n_groups;
+        const bool first = (t == 0), last = (t == p.n_tiles - 1);
+        const int64_t f0 = (int64_t)t * kTile;
+        const int len = (int)((f0 + kTile < p.n_frames) ? kTile : p.n_frames - f0);
+        const int c = g * kCg + lane;
+        const bool cvalid = c < C;
+        const int r0 = warp * R;
+        const int nrow = len - r0 < 0 ? 0 : (len - r0 > R ? R : len - r0);
+        const bool full = (nrow == R) && (g * kCg + kCg <= C);  // warp-uniform: no per-row predicates
+        const int64_t ld = C;
+
+        // ---- this warp's rows: R independent coalesced loads, scaled by the leading gains; rows past the end are zero
+        T x[R];
+        const T *src = p.in + (f0 + r0) * ld + c;
+        T *dst = p.out + (f0 + r0) * ld + c;
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < R; i++) x[i] = __ldcs(src + i * ld);
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; i++) x[i] = (cvalid && i < nrow) ? __ldcs(src + i * ld) : T(0);
+        }
+        if (p.g_load != T(1)) {
+#pragma unroll
+            for (int i = 0; i < R; i++) x[i] *= p.g_load;
+        }
+        double m_peak = 0.0, m_sumsq = 0.0;
+
+        if (p.has_bq) {
+            // ---- pass 1: zero-state end state of the sub-chunk (the zero rows past the end of a ragged chunk leave its sum
+            //      unused: only full tiles are chained, and the stream's final state comes out of pass 2)
+            {
+                double z0 = 0.0, z1 = 0.0, y0 = 0.0, y1 = 0.0;  // two accumulator pairs: shorter dependent chains
+#pragma unroll
+                for (int i = 0; i < R; i += 2) {
+                    const double xa = (double)x[i], xb = (double)x[i + 1];
+                    z0 = fma(p.wt[R - 1 - i][0], xa, z0);
+                    z1 = fma(p.wt[R - 1 - i][1], xa, z1);
+                    y0 = fma(p.wt[R - 2 - i][0], xb, y0);
+                    y1 = fma(p.wt[R - 2 - i][1], xb, y1);
+                }
+                *reinterpret_cast<double2 *>(zq_s + (warp * kCg + lane) * 2) = make_double2(z0 + y0, z1 + y1);
+            }
+            __syncthreads();
+            // ---- warp 0: the tile aggregate sum_q A^(R (7-q)) z_q, published at once (it depends on nothing) and parked in
+            //      shared memory until the inclusive state is due
+            const size_t slot = (size_t)g * p.n_tiles + t;
+            if (warp == 0) {
+                double Z0 = 0.0, Z1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < kStWarps; q++) {
+                    const double2 z = *reinterpret_cast<const double2 *>(zq_s + (q * kCg + lane) * 2);
+                    mat2_fma(pw_s + 4 * (kStWarps - 1 - q), z.x, z.y, Z0, Z1);
+                }
+                *reinterpret_cast<double2 *>(zsum_s + lane * 2) = make_double2(Z0, Z1);
+                if (!last && !first) {
+                    // payload by every lane, then ONE release by lane 0: the warp barrier orders the lanes' stores before it
+                    *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
+                    __syncwarp();
+                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
+                }
+            }
+            // ---- look-back: warp w resolves window w (tiles t-1-32w .. t-32-32w) of this group
+            {
+                double w0 = 0.0, w1 = 0.0;
+                int terminal = 1;
+                if (first) {
+                    if (warp == 0 && cvalid) {
+                        w0 = p.bq_state[2 * c];
+                        w1 = p.bq_state[2 * c + 1];
+                    }
+                } else {
+                    const unsigned *st_g = p.lb_status + (size_t)g * p.n_tiles;
+                    const double *agg_g = p.lb_agg + (size_t)g * p.n_tiles * 64, *inc_g = p.lb_inc + (size_t)g * p.n_tiles * 64;
+                    int base = t - 1 - kStWin * warp;
+                    if (base >= 0) {
+                        int first_inc = st_poll_window(st_g, base, lane, p.epoch, p.err_flag);
+                        __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
+                        if (first_inc >= 0) st_fold_window(agg_g, inc_g, lb_s, base, first_inc, lane, w0, w1);
+                        terminal = first_inc < kStWin;
+                        if (warp == kStWarps - 1 && !terminal) {
+                            const double2 r = st_slide(st_g, agg_g, inc_g, lb_s, base, lane, p.epoch, p.err_flag, w0, w1);
+                            w0 = r.x;
+                            w1 = r.y;
+                            terminal = 1;
+                        }
+                    }
+                }
+                *reinterpret_cast<double2 *>(part_s + (warp * kCg + lane) * 2) = make_double2(w0, w1);
+                if (lane == 0) flag_s[warp] = terminal;
+            }
+            __syncthreads();
+            // ---- incoming state of the tile: the windows' partials up to the first one that held an inclusive state
+            double S0 = 0.0, S1 = 0.0;
+#pragma unroll 1
+            for (int w = 0; w < kStWarps; w++) {
+                const double2 v = *reinterpret_cast<const double2 *>(part_s + (w * kCg + lane) * 2);
+                mat2_fma(mw_s + 4 * w, v.x, v.y, S0, S1);
+                if (flag_s[w]) break;
+            }
+            if (warp == 0 && !last) {
+                // inclusive state after this (full) tile
+                const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
+                double I0 = Z.x, I1 = Z.y;
+                mat2_fma(pw_s + 4 * kStWarps, S0, S1, I0, I1);
+                *reinterpret_cast<double2 *>(p.lb_inc + slot * 64 + lane * 2) = make_double2(I0, I1);
+                __syncwarp();
+                if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
+            }
+            // ---- pass 2: the recursion itself from the true state at the first row of the sub-chunk,
+            //      A^(R w) S + sum_{q<w} A^(R (w-1-q)) z_q
+            double s1 = 0.0, s2 = 0.0;
+            mat2_fma(pw_s + 4 * warp, S0, S1, s1, s2);
+#pragma unroll 1
+            for (int q = 0; q < warp; q++) {
+                const double2 z = *reinterpret_cast<const double2 *>(zq_s + (q * kCg + lane) * 2);
+                mat2_fma(pw_s + 4 * (warp - 1 - q), z.x, z.y, s1, s2);
+            }
+            if (full && !meter && !last) {
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const double xd = to_double_again(x[i]);
+                    const double v = fma(p.b0, xd, s1);
+                    s1 = fma(-p.a1, v, fma(p.b1, xd, s2));
+                    s2 = fma(-p.a2, v, p.b2 * xd);
+                    __stcs(dst + i * ld, (T)(v * p.g_bq));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const double xd = to_double_again(x[i]);
+                    const double v = fma(p.b0, xd, s1);
+                    s1 = fma(-p.a1, v, fma(p.b1, xd, s2));
+                    s2 = fma(-p.a2, v, p.b2 * xd);
+                    const T o = (T)(v * p.g_bq);
+                    if (i < nrow && cvalid) {  // rows past the end neither store nor reach the carried state
+                        __stcs(dst + i * ld, o);
+                        if (meter) {
+                            const double a = fabs((double)o);
+                            m_peak = a > m_peak ? a : m_peak;
+                            m_sumsq = fma((double)o, (double)o, m_sumsq);
+                        }
+                        if (last && r0 + i + 1 == len) {
+                            p.bq_state_next[2 * c] = s1;
+                            p.bq_state_next[2 * c + 1] = s2;
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; i++)
+                if (i < nrow && cvalid) {
+                    __stcs(dst + i * ld, x[i]);
+                    if (meter) {
+                        const double a = fabs((double)x[i]);
+                        m_peak = a > m_peak ? a : m_peak;
+                        m_sumsq = fma((double)x[i], (double)x[i], m_sumsq);
+                    }
+                }
+        }
+        if (meter) {
+            // zq_s is free again: its last readers (the prefix sums) are behind the barrier in front of pass 2
+            zq_s[(warp * kCg + lane) * 2] = m_peak;
+            zq_s[(warp * kCg + lane) * 2 + 1] = m_sumsq;
+            __syncthreads();
+            if (warp == 0 && cvalid) {
+                double pk = 0.0, sq = 0.0;
+#pragma unroll
+                for (int q = 0; q < kStWarps; q++) {
+                    const double a = zq_s[(q * kCg + lane) * 2];
+                    pk = a > pk ? a : pk;
+                    sq += zq_s[(q * kCg + lane) * 2 + 1];
+                }
+                atomic_max_nonneg(p.meter_peak + c, pk);
+                atomicAdd(p.meter_sumsq + c, sq);
+            }
+        }
+    }
+}
+
+// out = g * in over a flat buffer of n values (g == 1: a copy, bit-exact).  V is the 16-byte vector of T.
+template <typename T, typename V>
+__global__ void __launch_bounds__(256) stream_map_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t n, T g)
+{
+    constexpr int kPer = (int)(sizeof(V) / sizeof(T));
+    constexpr int kUnroll = 4;
+    const int64_t nv = n / kPer;
+    const V *vin = reinterpret_cast<const V *>(in);
+    V *vout = reinterpret_cast<V *>(out);
+    const bool scale = (g != T(1));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * kUnroll;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x * kUnroll + threadIdx.x; i < nv; i += stride) {
+        V v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++)
+            if (i + (int64_t)u * blockDim.x < nv) v[u] = __ldcs(vin + i + (int64_t)u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++)
+            if (i + (int64_t)u * blockDim.x < nv) {
+                if (scale) {
+                    T *e = reinterpret_cast<T *>(&v[u]);
+#pragma unroll
+                    for (int k = 0; k < kPer; k++) e[k] *= g;
+                }
+                __stcs(vout + i + (int64_t)u * blockDim.x, v[u]);
+            }
+    }
+    // tail (n not a multiple of the vector width)
+    const int64_t i = nv * kPer + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = scale ? in[i] * g : in[i];
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pb
