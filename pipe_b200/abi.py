@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libpipe_b200.so")
+LIB_PATH = os.environ.get("PB_LIB") or os.path.join(PKG_DIR, "libpipe_b200.so")  # PB_LIB: a tuning build of the same library
 
 ABI_VERSION = 1
 PB_OK = 0

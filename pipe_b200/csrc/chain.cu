@@ -709,8 +709,8 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     }
     if (s.st_ok) {
         int per_sm = 0;
-        if (f32) PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<float>, kStThreads, 0));
-        else PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<double>, kStThreads, 0));
+        if (f32) PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<float, 0>, kStThreads, 0));
+        else PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<double, 0>, kStThreads, 0));
         if (per_sm < 1) return fail(PB_ERR_UNSUPPORTED, "streaming kernel does not fit on an SM");
         s.st_grid = per_sm * c->num_sms;
     }
@@ -853,6 +853,7 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
     p.g_bq = has_bq ? g_back : 1.0;
     p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
     memcpy(p.wt, s.st_wt, sizeof(p.wt));
+    p.vec_ok = (c->C % (int)(16 / sizeof(T)) == 0 && ((uintptr_t)in % 16) == 0) ? 1 : 0;
     p.tab = (const double *)s.d_st_tab;
     p.bq_state = (const double *)s.d_state[s.pp];
     p.bq_state_next = (double *)s.d_state[s.pp ^ 1];
@@ -869,7 +870,11 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
     if (has_bq && p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int64_t total = (int64_t)p.n_tiles * p.n_groups;
     const int grid = (int)std::min<int64_t>(total, s.st_grid);
-    chain_stream_kernel<T><<<grid, kStThreads, 0, stream>>>(p);
+    // the channel counts of BASELINE.json's configs get row addresses with immediate offsets
+    if (c->C == 1024) chain_stream_kernel<T, 1024><<<grid, kStThreads, 0, stream>>>(p);
+    else if (c->C == 256) chain_stream_kernel<T, 256><<<grid, kStThreads, 0, stream>>>(p);
+    else if (c->C == 64) chain_stream_kernel<T, 64><<<grid, kStThreads, 0, stream>>>(p);
+    else chain_stream_kernel<T, 0><<<grid, kStThreads, 0, stream>>>(p);
     PB_CUDA(cudaGetLastError());
     c->ticket_base += (unsigned long long)total + (unsigned long long)grid;
     c->launches++;

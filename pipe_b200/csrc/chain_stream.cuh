@@ -34,12 +34,21 @@
 
 namespace pb {
 
+#ifndef PB_ST_ROWS32
+#define PB_ST_ROWS32 32   // rows per warp for f32 (tuning switches, see profiles/)
+#endif
+#ifndef PB_ST_SMEM
+#define PB_ST_SMEM 1      // 1: the tile waits in shared memory (cp.async), 0: in registers
+#endif
+#ifndef PB_ST_MINB
+#define PB_ST_MINB (PB_ST_SMEM ? 5 : 3)  // resident CTAs per SM the register budget is set for
+#endif
 constexpr int kStThreads = 256;
 constexpr int kStWarps = kStThreads / 32;        // 8 sub-chunks per tile, and 8 look-back windows
 constexpr int kStWin = 32;                       // look-back window (one predecessor per lane)
 template <typename T>
 struct StShape {
-    static constexpr int kRows = sizeof(T) == 4 ? 32 : 16;   // rows a warp keeps in registers
+    static constexpr int kRows = sizeof(T) == 4 ? PB_ST_ROWS32 : 16;   // rows a warp keeps in registers
     static constexpr int kTile = kStWarps * kRows;            // frames per tile: 256 (f32) / 128 (f64)
 };
 constexpr int kStMinTile = 128;
@@ -73,6 +82,7 @@ struct StreamParams {
     unsigned long long *ticket;
     unsigned long long ticket_base;
     int *err_flag;
+    int vec_ok;           // 16-byte copies usable: C a multiple of the vector width and `in` 16-byte aligned
 };
 
 #ifdef __CUDACC__
@@ -165,8 +175,10 @@ __device__ __noinline__ double2 st_slide(const unsigned *st_g, const double *agg
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __grid_constant__ StreamParams<T> p)
+// CC: the channel count when it is one of the instantiated constants (then every row address is base + immediate: the
+// 64-bit address arithmetic per row was a quarter of all instructions), 0 for any other count.
+template <typename T, int CC>
+__global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(const __grid_constant__ StreamParams<T> p)
 {
     constexpr int R = StShape<T>::kRows, kTile = StShape<T>::kTile;
     __shared__ double tab_s[StTab::kCount];
@@ -175,9 +187,12 @@ __global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __gri
     __shared__ double zsum_s[kCg * 2];             // tile aggregate, parked by warp 0 across the look-back
     __shared__ int flag_s[kStWarps];               // window w held an inclusive state (the combination stops there)
     __shared__ int s_tile;
+#if PB_ST_SMEM
+    __shared__ __align__(16) T xs[kStWarps * R * kCg];  // 32 KB: the tile, one slab of R rows per warp
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = p.C;
+    const int C = CC ? CC : p.C;
     const int total_tiles = p.n_tiles * p.n_groups;
     const bool meter = p.meter_peak != nullptr;
     if (p.has_bq)
@@ -200,12 +215,57 @@ __global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __gri
         const int r0 = warp * R;
         const int nrow = len - r0 < 0 ? 0 : (len - r0 > R ? R : len - r0);
         const bool full = (nrow == R) && (g * kCg + kCg <= C);  // warp-uniform: no per-row predicates
-        const int64_t ld = C;
+        const int64_t ld = C;  // a compile-time constant when CC != 0
 
+        T *dst = p.out + (f0 + r0) * ld + c;
+#if PB_ST_SMEM
+        // ---- this warp's rows go straight from HBM into shared memory (cp.async, no register staging): 16 B per lane, four
+        //      (f64: two) rows per instruction; rows past the end and channels past C are zero-filled (src-size 0).  The
+        //      leading gains are applied when a row is read.
+        T *xs_w = xs + warp * R * kCg;
+        {
+            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(xs_w);
+            if (p.vec_ok) {
+                constexpr int EPC = 16 / (int)sizeof(T), CPR = kCg / EPC, RPI = 32 / CPR;
+                const int rr = lane / CPR, ch = (lane % CPR) * EPC;
+                const bool chv = g * kCg + ch < C;
+#pragma unroll
+                for (int k = 0; k < R / RPI; k++) {
+                    const int row = k * RPI + rr;
+                    const bool ok = chv && row < nrow;
+                    const T *sp = ok ? p.in + (f0 + r0 + row) * ld + g * kCg + ch : p.in;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + (uint32_t)((row * kCg + ch) * sizeof(T))), "l"(sp),
+                                 "r"(ok ? 16 : 0)
+                                 : "memory");
+                }
+            } else if (sizeof(T) == 4) {
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const bool ok = cvalid && i < nrow;
+                    const T *sp = ok ? p.in + (f0 + r0 + i) * ld + c : p.in;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + (uint32_t)((i * kCg + lane) * sizeof(T))), "l"(sp),
+                                 "r"(ok ? 4 : 0)
+                                 : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const bool ok = cvalid && i < nrow;
+                    const T *sp = ok ? p.in + (f0 + r0 + i) * ld + c : p.in;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sbase + (uint32_t)((i * kCg + lane) * sizeof(T))), "l"(sp),
+                                 "r"(ok ? 8 : 0)
+                                 : "memory");
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();  // a row is read by other lanes than the ones that copied it
+        }
+        const T gl = p.g_load;
+#define PB_XV(i) (xs_w[(i) * kCg + lane] * gl)
+#else
         // ---- this warp's rows: R independent coalesced loads, scaled by the leading gains; rows past the end are zero
         T x[R];
         const T *src = p.in + (f0 + r0) * ld + c;
-        T *dst = p.out + (f0 + r0) * ld + c;
         if (full) {
 #pragma unroll
             for (int i = 0; i < R; i++) x[i] = __ldcs(src + i * ld);
@@ -217,6 +277,8 @@ __global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < R; i++) x[i] *= p.g_load;
         }
+#define PB_XV(i) x[i]
+#endif
         double m_peak = 0.0, m_sumsq = 0.0;
 
         if (p.has_bq) {
@@ -226,7 +288,7 @@ __global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __gri
                 double z0 = 0.0, z1 = 0.0, y0 = 0.0, y1 = 0.0;  // two accumulator pairs: shorter dependent chains
 #pragma unroll
                 for (int i = 0; i < R; i += 2) {
-                    const double xa = (double)x[i], xb = (double)x[i + 1];
+                    const double xa = (double)PB_XV(i), xb = (double)PB_XV(i + 1);
                     z0 = fma(p.wt[R - 1 - i][0], xa, z0);
                     z1 = fma(p.wt[R - 1 - i][1], xa, z1);
                     y0 = fma(p.wt[R - 2 - i][0], xb, y0);
@@ -312,7 +374,7 @@ __global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __gri
             if (full && !meter && !last) {
 #pragma unroll
                 for (int i = 0; i < R; i++) {
-                    const double xd = to_double_again(x[i]);
+                    const double xd = to_double_again(PB_XV(i));
                     const double v = fma(p.b0, xd, s1);
                     s1 = fma(-p.a1, v, fma(p.b1, xd, s2));
                     s2 = fma(-p.a2, v, p.b2 * xd);
@@ -321,7 +383,7 @@ __global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __gri
             } else {
 #pragma unroll
                 for (int i = 0; i < R; i++) {
-                    const double xd = to_double_again(x[i]);
+                    const double xd = to_double_again(PB_XV(i));
                     const double v = fma(p.b0, xd, s1);
                     s1 = fma(-p.a1, v, fma(p.b1, xd, s2));
                     s2 = fma(-p.a2, v, p.b2 * xd);
@@ -344,11 +406,12 @@ __global__ void __launch_bounds__(kStThreads, 3) chain_stream_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < R; i++)
                 if (i < nrow && cvalid) {
-                    __stcs(dst + i * ld, x[i]);
+                    const T o = PB_XV(i);
+                    __stcs(dst + i * ld, o);
                     if (meter) {
-                        const double a = fabs((double)x[i]);
+                        const double a = fabs((double)o);
                         m_peak = a > m_peak ? a : m_peak;
-                        m_sumsq = fma((double)x[i], (double)x[i], m_sumsq);
+                        m_sumsq = fma((double)o, (double)o, m_sumsq);
                     }
                 }
         }
