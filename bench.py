@@ -183,6 +183,44 @@ def run_reference(args):
 
 # ---------------------------------------------------------------- CUDA arm --
 
+def hbm_bound_runs(local, stream):
+    """[gain, biquad] (configs[1]: 64 ch x 4096-frame buffers; and at 1024 ch) through the streaming kernels (K3):
+    8 B of HBM traffic per sample, batches larger than L2, CUDA events on the launching stream."""
+    import torch
+
+    from pipe_b200 import abi, design
+    peak, _ = measured_peak()
+    out = []
+    for name, ch, nb in (("configs[1]: Source->[gain, biquad-IIR]->Sink, 48 kHz x 64 ch float32, 4096-sample buffer", 64, 320),
+                         ("[gain, biquad-IIR] at 48 kHz x 1024 ch float32, 4096-sample buffer", 1024, 20)):
+        frames = BUFFER_FRAMES * nb
+        chain = abi.Chain(ch, design.config_stages("gain_biquad"), buffer_frames=BUFFER_FRAMES, max_batch=nb, device=local)
+        x = torch.empty((frames, ch), dtype=torch.float32, device=f"cuda:{local}")
+        y = torch.empty_like(x)
+        abi.source_fill(x.data_ptr(), abi.PB_F32, 0, frames * ch, seed=1234, line=0, device=local)
+        sizes = [BUFFER_FRAMES] * nb
+        for _ in range(3):
+            chain.process_batch_device(x.data_ptr(), sizes, y.data_ptr(), frames, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        steps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            chain.process_batch_device(x.data_ptr(), sizes, y.data_ptr(), frames, stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        chain.sync(stream.cuda_stream)
+        ms = e0.elapsed_time(e1) / steps
+        gbs = 8.0 * frames * ch / (ms * 1e-3) / 1e9
+        out.append({"workload": name, "value": frames * ch / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+                    "batch_buffers": nb, "kernel_path": {1: "generic fused tile kernel", 3: "streaming kernel"}.get(chain.last_path()[0]),
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                 "algorithmic_bytes_per_launch": 8.0 * frames * ch}})
+        chain.close()
+        del x, y
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -273,6 +311,10 @@ def run_cuda(args):
     else:
         e2e_ms = e2e_s * 1e3
 
+    # ---- the HBM-bound runs (configs[1] and the same run at 1024 ch) on the streaming kernels, device-resident; reported
+    #      beside the headline so that every BASELINE.json config that fits one GPU has a measured roofline fraction
+    secondary = hbm_bound_runs(local, stream) if (rank == 0 and world == 1 and not args.no_secondary) else None
+
     samples_step = frames * CHANNELS               # per rank
     value = world * samples_step * args.steps / (total_ms * 1e-3) / 1e6
     e2e_value = world * samples_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
@@ -282,7 +324,8 @@ def run_cuda(args):
         kern_ms = statistics.mean(step_ms)       # one fused launch per step on this stream
         achieved = samples_step * BYTES_PER_SAMPLE / (kern_ms * 1e-3) / 1e9
         cpu_threads = os.cpu_count() or 1
-        cpu_val, cpu_dt = cpu_chain_throughput(args.cpu_buffers, cpu_threads) if world == 1 or True else (None, None)
+        # the CPU baseline is timed at N = 1 only (the driver's scaling runs reuse that line)
+        cpu_val, cpu_dt = cpu_chain_throughput(args.cpu_buffers, cpu_threads) if world == 1 else (None, 0.0)
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -310,6 +353,8 @@ def run_cuda(args):
             "gpu_launches": int(launches1 - launches0),
             "clocks": clk,
         }
+        if secondary is not None:
+            line["secondary"] = secondary
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -323,8 +368,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch-buffers", type=int, default=BATCH_BUFFERS)
-    ap.add_argument("--cpu-buffers", type=int, default=20, help="bounded CPU-baseline sample (buffers)")
+    ap.add_argument("--cpu-buffers", type=int, default=300, help="bounded CPU-baseline sample (buffers): ~10 s on 16 threads")
     ap.add_argument("--meter", action="store_true", help="fuse the peak/RMS meter sink into the chain kernel")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the HBM-bound secondary runs (configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -197,6 +197,20 @@ static int32_t configure_kernel(pb_chain *c, Segment &s)
 }
 
 
+// K3: dynamic shared memory attribute of every instantiation (per function, per device) and the resident CTAs per SM
+template <typename T>
+static cudaError_t configure_stream_kernels(int *per_sm)
+{
+    cudaError_t e = cudaSuccess;
+    if (kStDynSmem > 0) {
+        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, chain_stream_kernel<T, 0>, kStThreads, kStDynSmem);
+}
+
 // ---- K2 host side --------------------------------------------------------------
 
 // fixed-point split: scale 2^shift so that |v| <= 2047 and sum|v| <= 8191 (with |x*2^10| <= 2048 every
@@ -709,8 +723,8 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     }
     if (s.st_ok) {
         int per_sm = 0;
-        if (f32) PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<float, 0>, kStThreads, 0));
-        else PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_stream_kernel<double, 0>, kStThreads, 0));
+        if (f32) PB_CUDA((configure_stream_kernels<float>(&per_sm)));
+        else PB_CUDA((configure_stream_kernels<double>(&per_sm)));
         if (per_sm < 1) return fail(PB_ERR_UNSUPPORTED, "streaming kernel does not fit on an SM");
         s.st_grid = per_sm * c->num_sms;
     }
@@ -871,12 +885,12 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
     const int64_t total = (int64_t)p.n_tiles * p.n_groups;
     const int grid = (int)std::min<int64_t>(total, s.st_grid);
     // the channel counts of BASELINE.json's configs get row addresses with immediate offsets
-    if (c->C == 1024) chain_stream_kernel<T, 1024><<<grid, kStThreads, 0, stream>>>(p);
-    else if (c->C == 256) chain_stream_kernel<T, 256><<<grid, kStThreads, 0, stream>>>(p);
-    else if (c->C == 64) chain_stream_kernel<T, 64><<<grid, kStThreads, 0, stream>>>(p);
-    else chain_stream_kernel<T, 0><<<grid, kStThreads, 0, stream>>>(p);
+    if (c->C == 1024) chain_stream_kernel<T, 1024><<<grid, kStThreads, kStDynSmem, stream>>>(p);
+    else if (c->C == 256) chain_stream_kernel<T, 256><<<grid, kStThreads, kStDynSmem, stream>>>(p);
+    else if (c->C == 64) chain_stream_kernel<T, 64><<<grid, kStThreads, kStDynSmem, stream>>>(p);
+    else chain_stream_kernel<T, 0><<<grid, kStThreads, kStDynSmem, stream>>>(p);
     PB_CUDA(cudaGetLastError());
-    c->ticket_base += (unsigned long long)total + (unsigned long long)grid;
+    c->ticket_base += (unsigned long long)total + (unsigned long long)grid * kStTicketsPerCta;
     c->launches++;
     if (has_bq) s.pp ^= 1;
     return PB_OK;

@@ -17,7 +17,7 @@
 //                         look-back latency is what bounds an HBM-bound tile kernel (measured: 60-80 % of a tile's time
 //                         with one warp walking predecessors while the others wait at a barrier):
 //                           * sub-chunk prefix states are computed by every warp in parallel from a table of A^(R j);
-//                           * ALL 8 warps look back, warp w over the window of 32 predecessors [32 w, 32 w + 32): each
+//                           * ALL 8 warps look back, each over one window of 32 predecessors [32 w, 32 w + 32): each
 //                             folds its window (independent FMAs against a table of (A^T)^i) and the partial results are
 //                             combined up to the first window that held an inclusive state.  A tile therefore never waits
 //                             for an inclusive state to appear, only for aggregates, which depend on nothing -- with few
@@ -37,12 +37,18 @@ namespace pb {
 #ifndef PB_ST_ROWS32
 #define PB_ST_ROWS32 32   // rows per warp for f32 (tuning switches, see profiles/)
 #endif
+// Where a tile waits between its two passes (measured on gain + biquad, 1024 ch f32, profiles/r01_k3_summary.md):
+//   1  in shared memory, copied there by cp.async, 5 CTAs per SM                                  65 % of the HBM peak
+//   0  in registers (32 rows per thread), 3 CTAs per SM                                           57 %
+//   2  two tiles in shared memory, the next tile's copies and ticket in flight, 3 CTAs per SM     40 %: a CTA that holds
+//      a ticket it is not yet working on publishes that tile's aggregate a whole tile late, and its successors wait
 #ifndef PB_ST_SMEM
-#define PB_ST_SMEM 1      // 1: the tile waits in shared memory (cp.async), 0: in registers
+#define PB_ST_SMEM 1
 #endif
 #ifndef PB_ST_MINB
-#define PB_ST_MINB (PB_ST_SMEM ? 5 : 3)  // resident CTAs per SM the register budget is set for
+#define PB_ST_MINB (PB_ST_SMEM == 2 ? 3 : PB_ST_SMEM ? 5 : 3)  // resident CTAs per SM the register budget is set for
 #endif
+constexpr int kStTicketsPerCta = PB_ST_SMEM == 2 ? 2 : 1;  // tickets a CTA draws past the end of the batch
 constexpr int kStThreads = 256;
 constexpr int kStWarps = kStThreads / 32;        // 8 sub-chunks per tile, and 8 look-back windows
 constexpr int kStWin = 32;                       // look-back window (one predecessor per lane)
@@ -52,6 +58,7 @@ struct StShape {
     static constexpr int kTile = kStWarps * kRows;            // frames per tile: 256 (f32) / 128 (f64)
 };
 constexpr int kStMinTile = 128;
+constexpr int kStDynSmem = PB_ST_SMEM == 2 ? 2 * 32 * 1024 : 0;  // both dtypes: 8 warps x R rows x 32 channels = 32 KB per tile
 
 // double tables in global memory, copied to shared memory at kernel start (dynamic indices)
 struct StTab {
@@ -175,6 +182,50 @@ __device__ __noinline__ double2 st_slide(const unsigned *st_g, const double *agg
     }
 }
 
+// This warp's rows of `tile` go straight from HBM into its slab of shared memory (cp.async, no register staging): 16 B per
+// lane, four (f64: two) rows per instruction; rows past the end and channels past C are zero-filled (src-size 0).
+template <typename T>
+__device__ __forceinline__ void st_issue_tile(const StreamParams<T> &p, int C, int tile, T *xs_w, int warp, int lane)
+{
+    constexpr int R = StShape<T>::kRows, kTile = StShape<T>::kTile;
+    const int t = tile / p.n_groups, g = tile - t * p.n_groups;
+    const int64_t f0 = (int64_t)t * kTile, ld = C;
+    const int len = (int)((f0 + kTile < p.n_frames) ? kTile : p.n_frames - f0);
+    const int r0 = warp * R;
+    const int nrow = len - r0 < 0 ? 0 : (len - r0 > R ? R : len - r0);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(xs_w);
+    if (p.vec_ok) {
+        constexpr int EPC = 16 / (int)sizeof(T), CPR = kCg / EPC, RPI = 32 / CPR;
+        const int rr = lane / CPR, ch = (lane % CPR) * EPC;
+        const bool chv = g * kCg + ch < C;
+        const T *sp0 = p.in + (f0 + r0 + rr) * ld + g * kCg + ch;
+#pragma unroll
+        for (int k = 0; k < R / RPI; k++) {
+            const int row = k * RPI + rr;
+            const bool ok = chv && row < nrow;
+            const T *sp = ok ? sp0 + (int64_t)(k * RPI) * ld : p.in;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + (uint32_t)((row * kCg + ch) * sizeof(T))), "l"(sp),
+                         "r"(ok ? 16 : 0)
+                         : "memory");
+        }
+    } else {
+        const int c = g * kCg + lane;
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const bool ok = c < C && i < nrow;
+            const T *sp = ok ? p.in + (f0 + r0 + i) * ld + c : p.in;
+            if (sizeof(T) == 4)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + (uint32_t)((i * kCg + lane) * sizeof(T))), "l"(sp),
+                             "r"(ok ? 4 : 0)
+                             : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sbase + (uint32_t)((i * kCg + lane) * sizeof(T))), "l"(sp),
+                             "r"(ok ? 8 : 0)
+                             : "memory");
+        }
+    }
+}
+
 // CC: the channel count when it is one of the instantiated constants (then every row address is base + immediate: the
 // 64-bit address arithmetic per row was a quarter of all instructions), 0 for any other count.
 template <typename T, int CC>
@@ -186,9 +237,15 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
     __shared__ double part_s[kStWarps * kCg * 2];  // look-back partial of every window
     __shared__ double zsum_s[kCg * 2];             // tile aggregate, parked by warp 0 across the look-back
     __shared__ int flag_s[kStWarps];               // window w held an inclusive state (the combination stops there)
+#if PB_ST_SMEM == 2
+    __shared__ int s_next[2];
+    extern __shared__ __align__(16) unsigned char xs_raw[];  // 2 x 32 KB: two tiles, one slab of R rows per warp in each
+    T *xs = reinterpret_cast<T *>(xs_raw);
+#elif PB_ST_SMEM
     __shared__ int s_tile;
-#if PB_ST_SMEM
     __shared__ __align__(16) T xs[kStWarps * R * kCg];  // 32 KB: the tile, one slab of R rows per warp
+#else
+    __shared__ int s_tile;
 #endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -199,12 +256,42 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
         for (int i = tid; i < StTab::kCount; i += kStThreads) tab_s[i] = p.tab[i];
     const double *pw_s = tab_s + StTab::kPw, *lb_s = tab_s + StTab::kLb, *mw_s = tab_s + StTab::kMw;
 
+#if PB_ST_SMEM == 2
+    // Software pipeline over this CTA's tiles: the copies of the NEXT tile are in flight while the current one is processed,
+    // and the ticket after that is already being fetched.  s_next[k & 1] holds the ticket of the CTA's k-th tile.
+    if (tid == 0) {
+        s_next[0] = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+        s_next[1] = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+    }
+    __syncthreads();
+    if (s_next[0] < total_tiles) st_issue_tile<T>(p, C, s_next[0], xs + warp * R * kCg, warp, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int k = 0;; k++) {
+        const int tile = s_next[k & 1];
+        if (tile >= total_tiles) break;
+        __syncthreads();  // every thread has read s_next[k & 1]; the previous tile is done with the small shared arrays
+        const int nxt = s_next[(k + 1) & 1];
+        if (tid == 0) s_next[k & 1] = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);  // the CTA's tile k + 2
+        // a warp's slab is read by that warp only, so the buffer of tile k - 1 is free in program order
+        if (nxt < total_tiles) st_issue_tile<T>(p, C, nxt, xs + (((k + 1) & 1) * kStWarps + warp) * R * kCg, warp, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's copies have landed
+        __syncwarp();  // a row is read by other lanes than the ones that copied it
+        T *xs_w = xs + ((k & 1) * kStWarps + warp) * R * kCg;
+#else
     for (;;) {
         __syncthreads();  // previous tile done with shared memory (and the tables visible)
         if (tid == 0) s_tile = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
         __syncthreads();
         const int tile = s_tile;
         if (tile >= total_tiles) break;
+#if PB_ST_SMEM
+        T *xs_w = xs + warp * R * kCg;
+        st_issue_tile<T>(p, C, tile, xs_w, warp, lane);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();  // a row is read by other lanes than the ones that copied it
+#endif
+#endif
         // time-major tickets: a tile only waits on smaller tickets, which resident CTAs already hold
         const int t = tile / p.n_groups, g = tile - t * p.n_groups;
         const bool first = (t == 0), last = (t == p.n_tiles - 1);
@@ -219,48 +306,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
 
         T *dst = p.out + (f0 + r0) * ld + c;
 #if PB_ST_SMEM
-        // ---- this warp's rows go straight from HBM into shared memory (cp.async, no register staging): 16 B per lane, four
-        //      (f64: two) rows per instruction; rows past the end and channels past C are zero-filled (src-size 0).  The
-        //      leading gains are applied when a row is read.
-        T *xs_w = xs + warp * R * kCg;
-        {
-            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(xs_w);
-            if (p.vec_ok) {
-                constexpr int EPC = 16 / (int)sizeof(T), CPR = kCg / EPC, RPI = 32 / CPR;
-                const int rr = lane / CPR, ch = (lane % CPR) * EPC;
-                const bool chv = g * kCg + ch < C;
-#pragma unroll
-                for (int k = 0; k < R / RPI; k++) {
-                    const int row = k * RPI + rr;
-                    const bool ok = chv && row < nrow;
-                    const T *sp = ok ? p.in + (f0 + r0 + row) * ld + g * kCg + ch : p.in;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + (uint32_t)((row * kCg + ch) * sizeof(T))), "l"(sp),
-                                 "r"(ok ? 16 : 0)
-                                 : "memory");
-                }
-            } else if (sizeof(T) == 4) {
-#pragma unroll
-                for (int i = 0; i < R; i++) {
-                    const bool ok = cvalid && i < nrow;
-                    const T *sp = ok ? p.in + (f0 + r0 + i) * ld + c : p.in;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sbase + (uint32_t)((i * kCg + lane) * sizeof(T))), "l"(sp),
-                                 "r"(ok ? 4 : 0)
-                                 : "memory");
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < R; i++) {
-                    const bool ok = cvalid && i < nrow;
-                    const T *sp = ok ? p.in + (f0 + r0 + i) * ld + c : p.in;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sbase + (uint32_t)((i * kCg + lane) * sizeof(T))), "l"(sp),
-                                 "r"(ok ? 8 : 0)
-                                 : "memory");
-                }
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncwarp();  // a row is read by other lanes than the ones that copied it
-        }
-        const T gl = p.g_load;
+        const T gl = p.g_load;  // the leading gains are applied when a row is read
 #define PB_XV(i) (xs_w[(i) * kCg + lane] * gl)
 #else
         // ---- this warp's rows: R independent coalesced loads, scaled by the leading gains; rows past the end are zero
@@ -315,25 +361,28 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                     if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
                 }
             }
-            // ---- look-back: warp w resolves window w (tiles t-1-32w .. t-32-32w) of this group
+            // ---- look-back: every warp resolves one window of 32 predecessors of this group.  Warp 0 has just paid for the
+            //      aggregate and its release, so it takes the farthest window (almost always one inclusive state, a single
+            //      load) and warp 1 the nearest, which holds the most aggregates.
             {
+                const int win = (warp + kStWarps - 1) % kStWarps;  // tiles t-1-32 win .. t-32-32 win
                 double w0 = 0.0, w1 = 0.0;
                 int terminal = 1;
                 if (first) {
-                    if (warp == 0 && cvalid) {
+                    if (win == 0 && cvalid) {
                         w0 = p.bq_state[2 * c];
                         w1 = p.bq_state[2 * c + 1];
                     }
                 } else {
                     const unsigned *st_g = p.lb_status + (size_t)g * p.n_tiles;
                     const double *agg_g = p.lb_agg + (size_t)g * p.n_tiles * 64, *inc_g = p.lb_inc + (size_t)g * p.n_tiles * 64;
-                    int base = t - 1 - kStWin * warp;
+                    const int base = t - 1 - kStWin * win;
                     if (base >= 0) {
-                        int first_inc = st_poll_window(st_g, base, lane, p.epoch, p.err_flag);
+                        const int first_inc = st_poll_window(st_g, base, lane, p.epoch, p.err_flag);
                         __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
                         if (first_inc >= 0) st_fold_window(agg_g, inc_g, lb_s, base, first_inc, lane, w0, w1);
                         terminal = first_inc < kStWin;
-                        if (warp == kStWarps - 1 && !terminal) {
+                        if (win == kStWarps - 1 && !terminal) {
                             const double2 r = st_slide(st_g, agg_g, inc_g, lb_s, base, lane, p.epoch, p.err_flag, w0, w1);
                             w0 = r.x;
                             w1 = r.y;
@@ -341,8 +390,8 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                         }
                     }
                 }
-                *reinterpret_cast<double2 *>(part_s + (warp * kCg + lane) * 2) = make_double2(w0, w1);
-                if (lane == 0) flag_s[warp] = terminal;
+                *reinterpret_cast<double2 *>(part_s + (win * kCg + lane) * 2) = make_double2(w0, w1);
+                if (lane == 0) flag_s[win] = terminal;
             }
             __syncthreads();
             // ---- incoming state of the tile: the windows' partials up to the first one that held an inclusive state
