@@ -361,11 +361,10 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                     if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
                 }
             }
-            // ---- look-back: every warp resolves one window of 32 predecessors of this group.  Warp 0 has just paid for the
-            //      aggregate and its release, so it takes the farthest window (almost always one inclusive state, a single
-            //      load) and warp 1 the nearest, which holds the most aggregates.
+            // ---- look-back: warp w resolves window w of this group's predecessors (rotating the windows so that warp 0,
+            //      which has just paid for the aggregate and its release, takes the farthest one measured no gain)
             {
-                const int win = (warp + kStWarps - 1) % kStWarps;  // tiles t-1-32 win .. t-32-32 win
+                const int win = warp;  // tiles t-1-32 win .. t-32-32 win
                 double w0 = 0.0, w1 = 0.0;
                 int terminal = 1;
                 if (first) {
