@@ -633,7 +633,7 @@ static int32_t refresh_segment_params(pb_chain *c, Segment &s)
         PB_CUDA(upload<double>(s.d_wt, wt));
         if (s.st_ok) {
             // K3 tables (chain_stream.cuh), R rows per warp: A^k B for k < R (kernel parameters), A^(R j) for j <= 16,
-            // (A^T)^i for i <= 32 and (A^T)^(32 w) for w < 16 with the tile step T = 16 R
+            // (A^T)^i and (A^T)^(32 i) for i <= 32, with the tile step T = 8 R
             const int R = c->dtype == PB_F32 ? StShape<float>::kRows : StShape<double>::kRows;
             std::vector<double> tab((size_t)StTab::kCount);
             auto mul = [](const double *X, const double *Y, double *Z) {
@@ -658,7 +658,7 @@ static int32_t refresh_segment_params(pb_chain *c, Segment &s)
             }
             const double *A32 = &tab[StTab::kLb + 4 * kStWin];   // (A^T)^32
             double W[4] = {1, 0, 0, 1};
-            for (int w = 0; w < kStWarps; w++) {
+            for (int w = 0; w <= kStWin; w++) {
                 for (int e = 0; e < 4; e++) tab[StTab::kMw + 4 * w + e] = W[e];
                 mul(W, A32, W);
             }

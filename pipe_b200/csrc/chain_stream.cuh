@@ -45,6 +45,12 @@ namespace pb {
 #ifndef PB_ST_SMEM
 #define PB_ST_SMEM 1
 #endif
+// Look-back: 0 = every warp walks one window of 32 predecessors (default); 1 = two levels (blocks of 32 tiles, see st_poll).
+// The two-level walk reads 1/32 of the payloads but measured SLOWER (1024 ch: 53.6 % vs 64.7 %, configs[1]: 27.6 % vs 31.5 %):
+// every tile behind a block boundary waits for the closer's block fold, which is 8 dependent L2 round trips on one warp.
+#ifndef PB_ST_BLOCKS
+#define PB_ST_BLOCKS 0
+#endif
 #ifndef PB_ST_MINB
 #define PB_ST_MINB (PB_ST_SMEM == 2 ? 3 : PB_ST_SMEM ? 5 : 3)  // resident CTAs per SM the register budget is set for
 #endif
@@ -64,8 +70,8 @@ constexpr int kStDynSmem = PB_ST_SMEM == 2 ? 2 * 32 * 1024 : 0;  // both dtypes:
 struct StTab {
     static constexpr int kPw = 0;                          // [9][4]   A^(R j), j = 0..8  (j = 8: the tile step A^T)
     static constexpr int kLb = kPw + 4 * (kStWarps + 1);   // [33][4]  (A^T)^i, i = 0..32
-    static constexpr int kMw = kLb + 4 * (kStWin + 1);     // [8][4]   (A^T)^(32 w), w = 0..7
-    static constexpr int kCount = kMw + 4 * kStWarps;
+    static constexpr int kMw = kLb + 4 * (kStWin + 1);     // [33][4]  (A^T)^(32 i), i = 0..32
+    static constexpr int kCount = kMw + 4 * (kStWin + 1);
 };
 
 template <typename T>
@@ -179,6 +185,71 @@ __device__ __noinline__ double2 st_slide(const unsigned *st_g, const double *agg
         if (first_inc >= 0) st_fold_window(agg_g, inc_g, lb_s, base, first_inc, lane, v0, v1);
         mat2_fma(M, v0, v1, w0, w1);
         if (first_inc < kStWin) return make_double2(w0, w1);
+    }
+}
+
+// ---- two-level look-back (PB_ST_BLOCKS) ------------------------------------------------------------------------------------
+// Tiles are grouped in blocks of 32.  The last tile of a block (the "closer") publishes, in its aggregate slot, the fold of the
+// WHOLE block instead of its own aggregate.  A tile then resolves its incoming state from (a) the aggregates of the tiles in
+// front of it inside its own block (at most 31, stride 1) and (b) one entry per earlier block (stride 32): the block fold, or
+// the closer's inclusive state, which ends the walk.  With two channel groups several hundred tiles of a group are in flight:
+// walking them one by one cost 1.9 GB of L2 reads per 0.34 GB of input (configs[1]); the block hops need 1/32 of that.
+
+// Lane i watches tile base - i * stride, for i < limit.  Returns the position of the first inclusive state, or `limit` when
+// all `limit` positions hold aggregates; -1 on timeout.  Positions before the stream start (tile index < 0) count as
+// inclusive: their payload is the state the call started from.  ignore_inc: the closer folds its block's aggregates only.
+__device__ __forceinline__ int st_poll(const unsigned *st_g, int base, int stride, int limit, bool ignore_inc, int lane, unsigned epoch,
+                                       int *err_flag)
+{
+    const int j = base - lane * stride;
+    for (unsigned spins = 0;; spins++) {
+        unsigned st = kLbAgg;  // lanes past the limit: ready, never inclusive
+        if (lane < limit) {
+            st = kLbInc;
+            if (j >= 0) {
+                st = ld_acquire_u32(st_g + j);
+                st = ((st >> 2) == epoch) ? (st & 3u) : kLbNone;
+                if (ignore_inc && st == kLbInc) st = kLbAgg;
+            }
+        }
+        const unsigned ready = __ballot_sync(0xffffffffu, st != kLbNone);
+        const unsigned inc = __ballot_sync(0xffffffffu, st == kLbInc);
+        if (inc) {
+            const int first_inc = __ffs(inc) - 1;
+            const unsigned need = (first_inc == 0) ? 0u : (0xffffffffu >> (32 - first_inc));
+            if ((ready & need) == need) return first_inc;
+        } else if (ready == 0xffffffffu) {
+            return limit;
+        }
+        if (spins > (1u << 24)) {  // ~1 s: a predecessor never published
+            if (lane == 0) atomicExch(err_flag, 1);
+            return -1;
+        }
+        __nanosleep(32);
+    }
+}
+
+// w += sum_{i < count} mt[i] Z_{base - i stride}  (+ mt[count] Inc_{base - count stride} when terminal), this lane's channel
+__device__ __forceinline__ void st_fold(const double *agg_g, const double *inc_g, const double *init, const double *mt, int base, int stride,
+                                        int count, bool terminal, int lane, double &w0, double &w1)
+{
+#pragma unroll 1
+    for (int i0 = 0; i0 < count; i0 += 4) {  // payloads four at a time: one L2 round trip per batch is exposed
+        double2 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = (i0 + u < count) ? i0 + u : count - 1;
+            a[u] = __ldcg(reinterpret_cast<const double2 *>(agg_g + (size_t)(base - i * stride) * 64 + lane * 2));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u < count) mat2_fma(mt + 4 * (i0 + u), a[u].x, a[u].y, w0, w1);
+    }
+    if (terminal) {
+        const int jt = base - count * stride;
+        const double2 q = jt < 0 ? (init ? *reinterpret_cast<const double2 *>(init) : make_double2(0.0, 0.0))
+                                 : __ldcg(reinterpret_cast<const double2 *>(inc_g + (size_t)jt * 64 + lane * 2));
+        mat2_fma(mt + 4 * count, q.x, q.y, w0, w1);
     }
 }
 
@@ -354,13 +425,87 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                     mat2_fma(pw_s + 4 * (kStWarps - 1 - q), z.x, z.y, Z0, Z1);
                 }
                 *reinterpret_cast<double2 *>(zsum_s + lane * 2) = make_double2(Z0, Z1);
+#if PB_ST_BLOCKS
+                // the closer of a block publishes the fold of the whole block, once it has it (below); the stream's first
+                // tile leaves its payload for the closer of block 0 and goes straight to an inclusive state
+                if (!last && (t & 31) != 31) {
+                    *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
+                    __syncwarp();
+                    if (lane == 0 && !first) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
+                }
+#else
                 if (!last && !first) {
                     // payload by every lane, then ONE release by lane 0: the warp barrier orders the lanes' stores before it
                     *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
                     __syncwarp();
                     if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
                 }
+#endif
             }
+#if PB_ST_BLOCKS
+            // ---- look-back, two levels: warp 0 walks the tiles in front of this one inside its block, warp 1 hops over the
+            //      earlier blocks (see st_poll)
+            const int m_own = t & 31;
+            if (warp < 2) {
+                const unsigned *st_g = p.lb_status + (size_t)g * p.n_tiles;
+                const double *agg_g = p.lb_agg + (size_t)g * p.n_tiles * 64, *inc_g = p.lb_inc + (size_t)g * p.n_tiles * 64;
+                const double *init = cvalid ? p.bq_state + 2 * c : nullptr;
+                double w0 = 0.0, w1 = 0.0;
+                int terminal = 1;
+                if (first) {
+                    if (warp == 0 && cvalid) {
+                        w0 = p.bq_state[2 * c];
+                        w1 = p.bq_state[2 * c + 1];
+                    }
+                } else if (warp == 0) {
+                    const bool closer = (m_own == 31);
+                    int fi = m_own ? st_poll(st_g, t - 1, 1, m_own, closer, lane, p.epoch, p.err_flag) : 0;
+                    __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
+                    if (fi < 0) fi = 0;
+                    terminal = fi < m_own;
+                    st_fold(agg_g, inc_g, init, lb_s, t - 1, 1, fi, terminal, lane, w0, w1);
+                    if (closer && !last) {
+                        // fold of the whole block: Z_t + A^T (fold of the 31 tiles in front)
+                        const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
+                        double B0 = Z.x, B1 = Z.y;
+                        mat2_fma(lb_s + 4, w0, w1, B0, B1);
+                        *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(B0, B1);
+                        __syncwarp();
+                        if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
+                    }
+                } else {
+                    // closers of the earlier blocks: tiles base, base - 32, ...; 32 hops per round (1024 tiles)
+                    double M[4] = {1.0, 0.0, 0.0, 1.0};
+                    for (int base = t - m_own - 1;; base -= 32 * kStWin) {
+                        int fi = st_poll(st_g, base, 32, kStWin, false, lane, p.epoch, p.err_flag);
+                        __syncwarp();
+                        if (fi < 0) break;
+                        double v0 = 0.0, v1 = 0.0;
+                        st_fold(agg_g, inc_g, init, mw_s, base, 32, fi, fi < kStWin, lane, v0, v1);
+                        mat2_fma(M, v0, v1, w0, w1);
+                        if (fi < kStWin) break;
+                        const double *ML = mw_s + 4 * kStWin;  // M <- M (A^T)^1024
+                        const double n0 = M[0] * ML[0] + M[1] * ML[2], n1 = M[0] * ML[1] + M[1] * ML[3];
+                        const double n2 = M[2] * ML[0] + M[3] * ML[2], n3 = M[2] * ML[1] + M[3] * ML[3];
+                        M[0] = n0; M[1] = n1; M[2] = n2; M[3] = n3;
+                    }
+                }
+                *reinterpret_cast<double2 *>(part_s + (warp * kCg + lane) * 2) = make_double2(w0, w1);
+                if (lane == 0) flag_s[warp] = terminal;
+            }
+            __syncthreads();
+            // ---- incoming state of the tile: own block, then (A^T)^m_own times what the hops found
+            double S0, S1;
+            {
+                const double2 v = *reinterpret_cast<const double2 *>(part_s + lane * 2);
+                S0 = v.x;
+                S1 = v.y;
+                if (!flag_s[0]) {
+                    const double2 h = *reinterpret_cast<const double2 *>(part_s + (kCg + lane) * 2);
+                    mat2_fma(lb_s + 4 * m_own, h.x, h.y, S0, S1);
+                }
+            }
+#else
             // ---- look-back: warp w resolves window w of this group's predecessors (rotating the windows so that warp 0,
             //      which has just paid for the aggregate and its release, takes the farthest one measured no gain)
             {
@@ -401,6 +546,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                 mat2_fma(mw_s + 4 * w, v.x, v.y, S0, S1);
                 if (flag_s[w]) break;
             }
+#endif
             if (warp == 0 && !last) {
                 // inclusive state after this (full) tile
                 const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
@@ -464,7 +610,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                 }
         }
         if (meter) {
-            // zq_s is free again: its last readers (the prefix sums) are behind the barrier in front of pass 2
+            __syncthreads();  // zq_s is reused: slower warps may still be reading the sub-chunk sums for their prefix
             zq_s[(warp * kCg + lane) * 2] = m_peak;
             zq_s[(warp * kCg + lane) * 2 + 1] = m_sumsq;
             __syncthreads();
