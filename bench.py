@@ -344,8 +344,9 @@ def run_cuda(args):
                          "algorithmic_bytes_per_launch": samples_step * BYTES_PER_SAMPLE,
                          "kernel_ms": kern_ms},
             "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cpu_threads, "kind": "port",
-                             "sample": f"{args.cpu_buffers} buffers of {BUFFER_FRAMES}x{CHANNELS} float64 through the "
-                                       f"C restatement (oracle/pipe_oracle.c), {cpu_threads} threads, {cpu_dt:.1f} s"},
+                             "sample": (f"{args.cpu_buffers} buffers of {BUFFER_FRAMES}x{CHANNELS} float64 through the "
+                                        f"C restatement (oracle/pipe_oracle.c), {cpu_threads} threads, {cpu_dt:.1f} s")
+                             if world == 1 else "not timed at N > 1: the CPU baseline is measured by the N = 1 run"},
             "e2e": {"value": e2e_value, "unit": "Msamples/s",
                     "h2d_bytes_per_step": frames * CHANNELS * 4, "d2h_bytes_per_step": out_frames * CHANNELS * 4,
                     "steps": e2e_steps, "path": "pb_chain_submit/collect, pinned host buffers, 2 batches in flight",
