@@ -3,14 +3,16 @@
 // i.e. BASELINE.json configs[0] (mock.Processor copy, reference mock/mock.go:147-154) and configs[1] (gain + biquad).
 // Like K1 they replace the ProcessFunc walk of Processor.execute (reference pipe.go:425-451, the call at :438) for the
 // run; unlike K1 these runs are HBM-bound (8 B per f32 sample, 16 B per f64 sample), so the kernels are built around
-// bytes in flight and instructions per row instead of shared-memory tiles:
+// bytes in flight, resident CTAs and the latency of the look-back:
 //
 //   stream_map_kernel     out = g * in over the flat buffer (copy / gain-only runs without meter): 16 B vectors,
 //                         four independent loads per thread before the first store, streaming cache hints.
 //   chain_stream_kernel   gain + biquad (+ fused meter sink).  A tile is 32 channels x 8 R frames (R = 32 for f32, 16 for
-//                         f64: 32 KB in, 32 KB out); each of the 8 warps holds its R rows IN REGISTERS (one coalesced
-//                         128 B / 256 B row per load instruction, nothing staged in shared memory), so one HBM read and one
-//                         HBM write per sample is all the traffic there is.  The biquad (TDF-II, double, the same carried
+//                         f64: 32 KB in, 32 KB out); the R rows of each of the 8 warps go from HBM straight into the warp's
+//                         slab of shared memory (cp.async, 16 B per lane, no register staging: 48 registers, 5 CTAs per SM),
+//                         are read from there by both passes and leave as one coalesced 128 B / 256 B store per row, so
+//                         one HBM read and one HBM write per sample is all the traffic there is (PB_ST_SMEM = 0 keeps the
+//                         rows in registers instead: 3 CTAs per SM, measured slower).  The biquad (TDF-II, double, the same carried
 //                         state [C][2] as K1/K2) is parallelised in time as in K1: zero-state end state of every R-row
 //                         sub-chunk (2 independent DFMA per sample), tile aggregate, decoupled look-back across tiles, the
 //                         true recursion from the resolved state (5 DFMA per sample).  What differs from K1, because the
