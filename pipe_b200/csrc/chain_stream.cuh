@@ -48,8 +48,9 @@ namespace pb {
 #define PB_ST_SMEM 1
 #endif
 // Look-back: 0 = every warp walks one window of 32 predecessors (default); 1 = two levels (blocks of 32 tiles, see st_poll).
-// The two-level walk reads 1/32 of the payloads but measured SLOWER (1024 ch: 53.6 % vs 64.7 %, configs[1]: 27.6 % vs 31.5 %):
-// every tile behind a block boundary waits for the closer's block fold, which is 8 dependent L2 round trips on one warp.
+// The two-level walk reads 1/32 of the payloads and needs one batch of payload loads per warp, yet it measured SLOWER
+// (1024 ch: 57.3 % vs 64.7 %, configs[1]: 27.6 % vs 31.5 %; with the own-block walk on one warp 53.6 %): the payload loads
+// are not what a tile waits for (profiles/r01_k3_summary.md).  Kept as a measured alternative.
 #ifndef PB_ST_BLOCKS
 #define PB_ST_BLOCKS 0
 #endif
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
     constexpr int R = StShape<T>::kRows, kTile = StShape<T>::kTile;
     __shared__ double tab_s[StTab::kCount];
     __shared__ double zq_s[kStWarps * kCg * 2];    // zero-state end state of every sub-chunk; reused for the meter partials
-    __shared__ double part_s[kStWarps * kCg * 2];  // look-back partial of every window
+    __shared__ double part_s[(kStWarps + 1) * kCg * 2];  // look-back partial of every window / slice (+ the hops)
     __shared__ double zsum_s[kCg * 2];             // tile aggregate, parked by warp 0 across the look-back
     __shared__ int flag_s[kStWarps];               // window w held an inclusive state (the combination stops there)
 #if PB_ST_SMEM == 2
@@ -445,65 +446,93 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
 #endif
             }
 #if PB_ST_BLOCKS
-            // ---- look-back, two levels: warp 0 walks the tiles in front of this one inside its block, warp 1 hops over the
-            //      earlier blocks (see st_poll)
+            // ---- look-back, two levels (see st_poll): the (at most 31) tiles in front of this one inside its block are cut
+            //      into slices of 4, one per warp -- one poll and one batch of payloads each, no exchange between the warps:
+            //      the combination below simply stops at the first slice that ended at an inclusive state; the last warp then
+            //      hops over the closers of the earlier blocks
             const int m_own = t & 31;
-            if (warp < 2) {
+            const bool closer = (m_own == 31);
+            {
                 const unsigned *st_g = p.lb_status + (size_t)g * p.n_tiles;
                 const double *agg_g = p.lb_agg + (size_t)g * p.n_tiles * 64, *inc_g = p.lb_inc + (size_t)g * p.n_tiles * 64;
                 const double *init = cvalid ? p.bq_state + 2 * c : nullptr;
                 double w0 = 0.0, w1 = 0.0;
-                int terminal = 1;
+                int terminal = 0;
                 if (first) {
-                    if (warp == 0 && cvalid) {
-                        w0 = p.bq_state[2 * c];
-                        w1 = p.bq_state[2 * c + 1];
-                    }
-                } else if (warp == 0) {
-                    const bool closer = (m_own == 31);
-                    int fi = m_own ? st_poll(st_g, t - 1, 1, m_own, closer, lane, p.epoch, p.err_flag) : 0;
-                    __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
-                    if (fi < 0) fi = 0;
-                    terminal = fi < m_own;
-                    st_fold(agg_g, inc_g, init, lb_s, t - 1, 1, fi, terminal, lane, w0, w1);
-                    if (closer && !last) {
-                        // fold of the whole block: Z_t + A^T (fold of the 31 tiles in front)
-                        const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
-                        double B0 = Z.x, B1 = Z.y;
-                        mat2_fma(lb_s + 4, w0, w1, B0, B1);
-                        *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(B0, B1);
-                        __syncwarp();
-                        if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
+                    if (warp == 0) {
+                        terminal = 1;
+                        if (cvalid) {
+                            w0 = p.bq_state[2 * c];
+                            w1 = p.bq_state[2 * c + 1];
+                        }
                     }
                 } else {
-                    // closers of the earlier blocks: tiles base, base - 32, ...; 32 hops per round (1024 tiles)
-                    double M[4] = {1.0, 0.0, 0.0, 1.0};
-                    for (int base = t - m_own - 1;; base -= 32 * kStWin) {
-                        int fi = st_poll(st_g, base, 32, kStWin, false, lane, p.epoch, p.err_flag);
-                        __syncwarp();
-                        if (fi < 0) break;
-                        double v0 = 0.0, v1 = 0.0;
-                        st_fold(agg_g, inc_g, init, mw_s, base, 32, fi, fi < kStWin, lane, v0, v1);
-                        mat2_fma(M, v0, v1, w0, w1);
-                        if (fi < kStWin) break;
-                        const double *ML = mw_s + 4 * kStWin;  // M <- M (A^T)^1024
-                        const double n0 = M[0] * ML[0] + M[1] * ML[2], n1 = M[0] * ML[1] + M[1] * ML[3];
-                        const double n2 = M[2] * ML[0] + M[3] * ML[2], n3 = M[2] * ML[1] + M[3] * ML[3];
-                        M[0] = n0; M[1] = n1; M[2] = n2; M[3] = n3;
+                    const int left = m_own - 4 * warp, cnt = left < 0 ? 0 : (left > 4 ? 4 : left);
+                    if (cnt > 0) {
+                        int fi = st_poll(st_g, t - 1 - 4 * warp, 1, cnt, closer, lane, p.epoch, p.err_flag);
+                        __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
+                        if (fi < 0) fi = 0;
+                        terminal = fi < cnt;
+                        st_fold(agg_g, inc_g, init, lb_s, t - 1 - 4 * warp, 1, fi, terminal, lane, w0, w1);
                     }
                 }
                 *reinterpret_cast<double2 *>(part_s + (warp * kCg + lane) * 2) = make_double2(w0, w1);
                 if (lane == 0) flag_s[warp] = terminal;
+                if (closer && !last) {
+                    // the closer publishes the fold of the whole block, Z_t + A^T (fold of the 31 tiles in front), BEFORE
+                    // the hops: the closers of later blocks must not wait for this tile's own look-back
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (warp == 0) {
+                        double W0 = 0.0, W1 = 0.0;
+#pragma unroll
+                        for (int q = 0; q < kStWarps; q++) {
+                            const double2 v = *reinterpret_cast<const double2 *>(part_s + (q * kCg + lane) * 2);
+                            mat2_fma(lb_s + 16 * q, v.x, v.y, W0, W1);
+                        }
+                        const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
+                        double B0 = Z.x, B1 = Z.y;
+                        mat2_fma(lb_s + 4, W0, W1, B0, B1);
+                        *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(B0, B1);
+                        __syncwarp();
+                        if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
+                    }
+                }
+                if (warp == kStWarps - 1) {
+                    // closers of the earlier blocks: tiles base, base - 32, ...; 32 hops per round (1024 tiles)
+                    double h0 = 0.0, h1 = 0.0;
+                    if (!first) {
+                        double M[4] = {1.0, 0.0, 0.0, 1.0};
+                        for (int base = t - m_own - 1;; base -= 32 * kStWin) {
+                            const int fi = st_poll(st_g, base, 32, kStWin, false, lane, p.epoch, p.err_flag);
+                            __syncwarp();
+                            if (fi < 0) break;
+                            double v0 = 0.0, v1 = 0.0;
+                            st_fold(agg_g, inc_g, init, mw_s, base, 32, fi, fi < kStWin, lane, v0, v1);
+                            mat2_fma(M, v0, v1, h0, h1);
+                            if (fi < kStWin) break;
+                            const double *ML = mw_s + 4 * kStWin;  // M <- M (A^T)^1024
+                            const double n0 = M[0] * ML[0] + M[1] * ML[2], n1 = M[0] * ML[1] + M[1] * ML[3];
+                            const double n2 = M[2] * ML[0] + M[3] * ML[2], n3 = M[2] * ML[1] + M[3] * ML[3];
+                            M[0] = n0; M[1] = n1; M[2] = n2; M[3] = n3;
+                        }
+                    }
+                    *reinterpret_cast<double2 *>(part_s + (kStWarps * kCg + lane) * 2) = make_double2(h0, h1);
+                }
             }
             __syncthreads();
-            // ---- incoming state of the tile: own block, then (A^T)^m_own times what the hops found
-            double S0, S1;
+            // ---- incoming state of the tile: the slices in order up to the first one that ended at an inclusive state;
+            //      if none did, (A^T)^m_own times what the hops found
+            double S0 = 0.0, S1 = 0.0;
             {
-                const double2 v = *reinterpret_cast<const double2 *>(part_s + lane * 2);
-                S0 = v.x;
-                S1 = v.y;
-                if (!flag_s[0]) {
-                    const double2 h = *reinterpret_cast<const double2 *>(part_s + (kCg + lane) * 2);
+                bool term = false;
+#pragma unroll 1
+                for (int q = 0; q < kStWarps && !term; q++) {
+                    const double2 v = *reinterpret_cast<const double2 *>(part_s + (q * kCg + lane) * 2);
+                    mat2_fma(lb_s + 16 * q, v.x, v.y, S0, S1);
+                    term = flag_s[q] != 0;
+                }
+                if (!term) {
+                    const double2 h = *reinterpret_cast<const double2 *>(part_s + (kStWarps * kCg + lane) * 2);
                     mat2_fma(lb_s + 4 * m_own, h.x, h.y, S0, S1);
                 }
             }
