@@ -863,10 +863,15 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
     p.n_tiles = (int)ceil_div64(n, StShape<T>::kTile);
     p.n_groups = (c->C + kCg - 1) / kCg;
     p.has_bq = has_bq;
-    p.g_load = has_bq ? (T)g_front : (T)(g_front * g_back);
+    // biquad runs: the leading gains go into the input-side coefficients (b0, b1, b2 and A^k B), the trailing ones scale the
+    // double result; the carried state keeps K1's meaning (it is driven by g x)
+    p.g_load = has_bq ? (T)1 : (T)(g_front * g_back);
     p.g_bq = has_bq ? g_back : 1.0;
-    p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
-    memcpy(p.wt, s.st_wt, sizeof(p.wt));
+    p.b0 = s.b[0] * g_front; p.b1 = s.b[1] * g_front; p.b2 = s.b[2] * g_front; p.a1 = s.a[0]; p.a2 = s.a[1];
+    for (int k = 0; k < 32; k++) {
+        p.wt[k][0] = s.st_wt[k][0] * g_front;
+        p.wt[k][1] = s.st_wt[k][1] * g_front;
+    }
     p.vec_ok = (c->C % (int)(16 / sizeof(T)) == 0 && ((uintptr_t)in % 16) == 0) ? 1 : 0;
     p.tab = (const double *)s.d_st_tab;
     p.bq_state = (const double *)s.d_state[s.pp];

@@ -83,7 +83,8 @@ struct StreamParams {
     T *out;
     int64_t n_frames;
     int C, n_tiles, n_groups;
-    T g_load;             // gains in front of the biquad (all gains of the run when there is none), applied in T like K1
+    T g_load;             // all gains of a run without biquad, applied in T like K1; 1 for a biquad run, whose leading gains
+                          // the host folds into wt and b0, b1, b2 (in double, like the oracle's y = g x)
     double g_bq;          // gains behind the biquad, applied to the double result before the single rounding to T
     int has_bq;
     double b0, b1, b2, a1, a2;
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
 #if PB_ST_SMEM
         const T gl = p.g_load;  // the leading gains are applied when a row is read
 #define PB_XV(i) (xs_w[(i) * kCg + lane] * gl)
+#define PB_XR(i) xs_w[(i) * kCg + lane]  // biquad runs: the host folds the leading gains into wt and b0..b2 (one FMUL per read less)
 #else
         // ---- this warp's rows: R independent coalesced loads, scaled by the leading gains; rows past the end are zero
         T x[R];
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
             for (int i = 0; i < R; i++) x[i] *= p.g_load;
         }
 #define PB_XV(i) x[i]
+#define PB_XR(i) x[i]
 #endif
         double m_peak = 0.0, m_sumsq = 0.0;
 
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                 double z0 = 0.0, z1 = 0.0, y0 = 0.0, y1 = 0.0;  // two accumulator pairs: shorter dependent chains
 #pragma unroll
                 for (int i = 0; i < R; i += 2) {
-                    const double xa = (double)PB_XV(i), xb = (double)PB_XV(i + 1);
+                    const double xa = (double)PB_XR(i), xb = (double)PB_XR(i + 1);
                     z0 = fma(p.wt[R - 1 - i][0], xa, z0);
                     z1 = fma(p.wt[R - 1 - i][1], xa, z1);
                     y0 = fma(p.wt[R - 2 - i][0], xb, y0);
@@ -599,7 +602,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
             if (full && !meter && !last) {
 #pragma unroll
                 for (int i = 0; i < R; i++) {
-                    const double xd = to_double_again(PB_XV(i));
+                    const double xd = to_double_again(PB_XR(i));
                     const double v = fma(p.b0, xd, s1);
                     s1 = fma(-p.a1, v, fma(p.b1, xd, s2));
                     s2 = fma(-p.a2, v, p.b2 * xd);
@@ -608,7 +611,7 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
             } else {
 #pragma unroll
                 for (int i = 0; i < R; i++) {
-                    const double xd = to_double_again(PB_XV(i));
+                    const double xd = to_double_again(PB_XR(i));
                     const double v = fma(p.b0, xd, s1);
                     s1 = fma(-p.a1, v, fma(p.b1, xd, s2));
                     s2 = fma(-p.a2, v, p.b2 * xd);

@@ -3,7 +3,7 @@ measured HBM peak.  Run on a GPU box:  python tools/hbm_chains.py [--json out.js
 
 Cases (a step is one batch launch; every batch is larger than the 126 MB L2):
   configs[1]  gain + biquad, 64 ch x 4096-frame buffers, f32      (8 B per sample)
-  the same run at 1024 ch                                        (8 B per sample)
+  the same run at 1024 ch, f32 and f64                           (8 / 16 B per sample)
   gain only, 1024 ch f32                                         (8 B per sample)
   configs[0] at scale: mock.Processor copy, 2 ch f64             (16 B per sample)
   copy, 1024 ch f64                                              (16 B per sample)
