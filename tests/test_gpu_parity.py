@@ -568,3 +568,36 @@ def test_k3_meter_and_mutation():
     y = g.process(x[:300, :5].astype(np.float32))
     pk, sq, fr = g.meter_read()
     assert fr == 300 and np.array_equal(pk, np.abs(y.astype(np.float64)).max(axis=0))
+
+
+@pytest.mark.parametrize("channels,nb", [(64, 320), (1024, 20)])
+def test_k3_full_batch_at_baseline_size(channels, nb):
+    # configs[1] at the size bench.py / tools/hbm_chains.py time it (320 buffers x 4096 frames x 64 ch in ONE launch: 5120 tiles
+    # per channel group, hundreds of them in flight) and the same run at 1024 ch: every buffer against the oracle, and
+    # linearity -- an input scaled by a power of two gives the scaled output: no rounding depends on the exponent, only the
+    # order in which a tile folds its predecessors may differ between two launches (1e-16 in double, so at most a handful
+    # of the 84 M float32 results may land on the other side of a rounding boundary)
+    bf = 4096
+    stages = design.config_stages("gain_biquad")
+    x = signal_input(bf * nb, channels, seed=8)
+    ref = orc.Chain(channels, stages).process(x, threads=os.cpu_count() or 1)
+    xf = x.astype(np.float32)
+    gpu = abi.Chain(channels, stages, buffer_frames=bf, max_batch=nb)
+    d_in, d_out = abi.DeviceBuffer(xf.nbytes), abi.DeviceBuffer(xf.nbytes)
+    d_in.upload(xf)
+    counts = gpu.process_batch_device(d_in.ptr, [bf] * nb, d_out.ptr, len(x))
+    gpu.sync()
+    assert counts == [bf] * nb and gpu.last_path()[0] == 3
+    y = d_out.download((len(x), channels), np.float32)
+    for b in range(nb):
+        assert_parity(y[b * bf:(b + 1) * bf], ref[b * bf:(b + 1) * bf], REL_F32, f"buffer {b}")
+    gpu.reset()
+    d_in.upload(xf * np.float32(0.25))
+    gpu.process_batch_device(d_in.ptr, [bf] * nb, d_out.ptr, len(x))
+    gpu.sync()
+    y2 = d_out.download((len(x), channels), np.float32)
+    diff = y2 != y * np.float32(0.25)
+    assert int(diff.sum()) <= 16, f"{int(diff.sum())} values differ"
+    assert float(np.abs(y2 - y * np.float32(0.25)).max()) <= 2.0 ** -24 * float(np.abs(y).max())
+    d_in.free()
+    d_out.free()
