@@ -27,6 +27,6 @@ def margin(cfg, channels, frames, buffers, flags=0):
 
 if __name__ == "__main__":
     for cfg, ch, fr, nb in (("gain_biquad", 64, 4096, 4), ("chain4", 64, 4096, 3), ("chain4", 1024, 4096, 2)):
-        for flags in (0, abi.CHAIN_NO_TENSOR):
+        for flags in (0, abi.CHAIN_NO_TENSOR, abi.CHAIN_NO_STREAM):  # default paths, then K1 instead of K2, K1 instead of K3
             w, path = margin(cfg, ch, fr, nb, flags)
             print(f"{cfg:12s} {ch:5d} ch x {fr} x {nb}  flags={flags} path={path}  worst err/peak = {w:.3e}  (bar 1e-6)")
