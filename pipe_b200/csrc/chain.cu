@@ -951,14 +951,40 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
             Segment &s = c->segs[i];
             const bool lastseg = (i + 1 == c->segs.size());
             void *dst = lastseg ? out_dev : c->d_mid[i & 1];
-            // K2 needs the call aligned to 160-frame tiles (then the resampler phase is 0 at every tile start)
-            const bool use_tc = s.tc_ok && s.acc == 0 && n >= kTcFrames && n % kTcFrames == 0 && s.g[2] != 0.0 && s.tc_level_ok &&
-                                ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
-            int32_t r = use_tc       ? launch_segment_tc(c, s, src, n, dst, lastseg, stream)
-                        : s.st_ok    ? (c->dtype == PB_F32 ? launch_segment_stream<float, float4>(c, s, src, n, dst, lastseg, stream)
-                                                           : launch_segment_stream<double, double2>(c, s, src, n, dst, lastseg, stream))
-                        : c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, src, n, dst, lastseg, stream)
-                                             : launch_segment<double, 8>(c, s, src, n, dst, lastseg, stream);
+            auto generic = [&](const void *from, int64_t frames, void *to) -> int32_t {
+                return s.st_ok ? (c->dtype == PB_F32 ? launch_segment_stream<float, float4>(c, s, from, frames, to, lastseg, stream)
+                                                     : launch_segment_stream<double, double2>(c, s, from, frames, to, lastseg, stream))
+                       : c->dtype == PB_F32 ? launch_segment<float, 16>(c, s, from, frames, to, lastseg, stream)
+                                            : launch_segment<double, 8>(c, s, from, frames, to, lastseg, stream);
+            };
+            // K2 works on 160-frame tiles that start where the resampler phase is 0, i.e. at stream positions that are multiples
+            // of 160.  A call that does not start or end there (a 4096-frame buffer never does both) is cut into a head up to the
+            // next such position, the aligned middle and a tail; head and tail go through K1, which shares every piece of
+            // carried state with K2 (launches on one stream are ordered like separate calls).
+            const bool tc_eligible = s.tc_ok && s.g[2] != 0.0 && s.tc_level_ok && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
+            int64_t head = 0;
+            if (tc_eligible)
+                while (head < s.down && (s.acc + head * s.up) % s.down != 0) head++;
+            const int64_t mid = (tc_eligible && n - head >= kTcFrames) ? ((n - head) / kTcFrames) * kTcFrames : 0;
+            int32_t r = PB_OK;
+            if (mid > 0) {
+                const int64_t acc0 = s.acc, pieces[3] = {head, mid, n - head - mid};
+                const char *from = (const char *)src;
+                char *to = (char *)dst;
+                for (int k = 0; k < 3 && r == PB_OK; k++) {
+                    const int64_t len = pieces[k];
+                    if (len == 0) continue;
+                    r = (k == 1) ? launch_segment_tc(c, s, from, len, to, lastseg, stream) : generic(from, len, to);
+                    const int64_t tot = s.acc + len * s.up;  // the phase each piece starts from, restored below
+                    from += (size_t)len * c->C * c->elem;
+                    to += (size_t)(tot / s.down) * c->C * c->elem;
+                    s.acc = tot % s.down;
+                }
+                s.acc = acc0;  // committed for the whole call by count_outputs
+            } else {
+                r = generic(src, n, dst);
+            }
+            const bool use_tc = mid > 0;
             if (r != PB_OK) return r;
             path = std::max(path, use_tc ? 2 : s.st_ok ? 3 : 1);
             if (s.rs_stage >= 0) n = (s.acc + n * s.up) / s.down;  // s.acc is committed below, after every launch used it

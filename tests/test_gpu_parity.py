@@ -358,7 +358,8 @@ def test_k2_tensor_path_matches_oracle(channels, bf, nb):
 
 
 def test_k2_and_k1_share_carried_state():
-    # ragged calls fall back to K1 mid-stream; history, biquad state and resampler phase must carry across
+    # calls that do not start and end on K2's 160-frame grid are cut into a K1 head, a K2 middle and a K1 tail; calls with less
+    # than one aligned tile run on K1 alone; history, biquad state and resampler phase must carry across every hand-over
     ch = 128
     gpu, cpu = _k2_chain(ch, 1600, 1), orc.Chain(ch, design.config_stages("chain4"))
     paths = []
@@ -374,7 +375,7 @@ def test_k2_and_k1_share_carried_state():
         y = gpu.process(blk.astype(np.float32))
         paths.append(gpu.last_path()[0])
         assert_parity(y, ref, REL_F32, f"{n} frames", floor=run_peak)
-    assert paths == [2, 2, 1, 1, 2, 1, 1, 2]
+    assert paths == [2, 2, 1, 1, 2, 1, 2, 2]  # 1563 frames from position 4997: 123 on K1, then 1440 on K2
 
 
 def test_k2_no_tensor_flag_and_meter():
@@ -601,3 +602,21 @@ def test_k3_full_batch_at_baseline_size(channels, nb):
     assert float(np.abs(y2 - y * np.float32(0.25)).max()) <= 2.0 ** -24 * float(np.abs(y).max())
     d_in.free()
     d_out.free()
+
+
+def test_k2_serves_4096_frame_buffers_between_k1_head_and_tail():
+    # bufferSize 4096 is not a multiple of K2's 160-frame tile and the resampler phase returns to 0 only every fifth buffer:
+    # every call is cut into a K1 head (to the next multiple of 160 in the stream), a K2 middle and a K1 tail.  Bit-exact frame
+    # counts (3763, 3763, 3763, 3763, 3764, ...) and the 1e-6 bar on every buffer.
+    ch, bf = 128, 4096
+    st = design.config_stages("chain4")
+    gpu, cpu = abi.Chain(ch, st, buffer_frames=bf), orc.Chain(ch, st)
+    lens = []
+    for b in range(6):
+        x = signal_input(bf, ch, seed=30 + b)
+        ref = cpu.process(x)
+        y = gpu.process(x.astype(np.float32))
+        lens.append(len(y))
+        assert gpu.last_path()[0] == 2
+        assert_parity(y, ref, REL_F32, f"buffer {b}")
+    assert lens == [3763, 3763, 3763, 3763, 3764, 3763]
