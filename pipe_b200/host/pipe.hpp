@@ -430,6 +430,13 @@ public:
         return errors_.empty() ? Error::None() : errors_.front();
     }
 
+    ~Pipe()  // a Pipe dropped without Wait cancels its components and joins them
+    {
+        cancel_.store(true);
+        for (auto &t : threads_)
+            if (t.joinable()) t.join();
+    }
+
 private:
     Pipe() = default;
     void Fail(Error e)
