@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -55,12 +56,23 @@ struct Segment {
     float tc_Mb[2][kTcBlocks][4];
     double tc_Wb[4], tc_Wbi[4];
     bool tc_level_ok = true;                         // the biquad keeps the broadband level (see build_tc_tables)
+    double tc_fir_l1 = 0;                            // sum |h|: bounds the FIR output on the channel's grid (fp16 range of the f pieces)
+    // per-channel block exponent of K2 (chain_tc.cuh): two ping-pong copies of {sigma[C], 1/sigma[C]} and of the measured peaks
+    float *d_tc_scale = nullptr;                     // [2][2][C]
+    unsigned *d_tc_peak = nullptr;                   // [2][C]
+    int tc_k = 0;                                    // copy the next call's pass A reads
     std::vector<float> tc_rc;                        // [147 + 32][8] output correction per block state (see chain_tc.cuh)
     // K3 (streaming kernels): runs without FIR and without resampler
     bool st_ok = false;
     int st_grid = 0;
     void *d_st_tab = nullptr;                        // StTab
     double st_wt[32][2] = {};                        // A^k B, passed in the kernel parameters
+};
+
+struct TmapEntry {  // cached TMA descriptor of a [rows][C] f32 buffer (K2)
+    const void *base = nullptr;
+    int64_t rows = 0;
+    CUtensorMap map;
 };
 
 struct Slot {  // one in-flight batch of the pipelined host path
@@ -91,12 +103,14 @@ struct pb_chain {
     unsigned long long ticket_base = 0;
     unsigned epoch = 0;
     double *d_meter = nullptr;  // [2][C]: peak, sumsq
+    double *d_meter_scratch = nullptr;  // [2][C]: what pass A of a K2 call metered, until pass B accepts or drops it
     int64_t meter_frames = 0;
     cudaStream_t st_compute = nullptr, st_h2d = nullptr, st_d2h = nullptr;
     Slot slots[2];
     int slot_head = 0, slot_tail = 0, slots_busy = 0;
     int last_path = 0;
     int64_t launches = 0;
+    std::vector<TmapEntry> tmaps;
 };
 
 namespace pb {
@@ -174,7 +188,8 @@ static void plan_segments(pb_chain *c)
 static void free_segment(Segment &s)
 {
     void *ptrs[] = {s.d_taps, s.d_wt, s.d_apow, s.d_coef, s.d_xhist[0], s.d_xhist[1], s.d_yhist[0], s.d_yhist[1],
-                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables, s.d_tc_rc, s.d_st_tab};
+                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables, s.d_tc_rc, s.d_st_tab,
+                    (void *)s.d_tc_scale, (void *)s.d_tc_peak};
     for (void *p : ptrs)
         if (p) cudaFree(p);
 }
@@ -255,6 +270,8 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
         for (int i = 0; i < 4; i++) M[i] = N[i];
     }
     s.tc_sh = fixed_shift(h.data(), kTcMaxTaps);
+    s.tc_fir_l1 = 0;
+    for (double v : h) s.tc_fir_l1 += std::fabs(v);
     const double sh = std::ldexp(1.0, s.tc_sh);
     std::vector<__half> tab((size_t)TcTables::kHalfs);
     __half *T0 = tab.data(), *T1 = T0 + TcTables::kT, *T2 = T1 + TcTables::kT, *T3 = T2 + TcTables::kT;
@@ -444,10 +461,10 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
         }
         sim(Apow[16], s.tc_A16);  // block step in balanced coordinates
         for (int i = 0; i < 4; i++) s.tc_ALf[i] = Apow[kTcFrames - kTcHr][i];
-        for (int i = 0; i < 16; i++) {  // W A^(15-i) B / grid
+        for (int i = 0; i < 16; i++) {  // W A^(15-i) B
             const double z0 = Apow[15 - i][0] * B[0] + Apow[15 - i][1] * B[1], z1 = Apow[15 - i][2] * B[0] + Apow[15 - i][3] * B[1];
-            s.tc_Wz[i][0] = (float)((W[0] * z0 + W[1] * z1) / 2048.0);
-            s.tc_Wz[i][1] = (float)((W[2] * z0 + W[3] * z1) / 2048.0);
+            s.tc_Wz[i][0] = (float)(W[0] * z0 + W[1] * z1);
+            s.tc_Wz[i][1] = (float)(W[2] * z0 + W[3] * z1);
         }
     }
     return PB_OK;
@@ -470,44 +487,96 @@ static PFN_encodeTiled get_encode_tiled()
     return fn;
 }
 
-// 2-D f32 tensor map over a [rows][C] frame-major buffer, box 32 channels x 16 frames, 128 B swizzle
+// 2-D f32 tensor map over a [rows][C] frame-major buffer, box 128 channels x 16 frames (one K chunk of a K2 tile), no swizzle:
+// the converter threads read it one channel per lane, 128 B per warp and row
 static int32_t make_frame_map(CUtensorMap *map, const void *base, int C, int64_t rows)
 {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(PB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
     const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)C * 4};
-    const cuuint32_t box[2] = {32, 16};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcCh, 16};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PB_OK;
+}
+
+// Encoding a tensor map costs a driver call; a chain sees the same few (pointer, rows) pairs call after call (its two history
+// buffers, the caller's or the slots' input buffers), so the last few are kept.
+static int32_t cached_frame_map(pb_chain *c, CUtensorMap *out, const void *base, int64_t rows)
+{
+    for (auto &e : c->tmaps)
+        if (e.base == base && e.rows == rows) {
+            *out = e.map;
+            return PB_OK;
+        }
+    TmapEntry e;
+    e.base = base;
+    e.rows = rows;
+    int32_t r = make_frame_map(&e.map, base, c->C, rows);
+    if (r != PB_OK) return r;
+    if (c->tmaps.size() >= 16) c->tmaps.erase(c->tmaps.begin());
+    c->tmaps.push_back(e);
+    *out = e.map;
     return PB_OK;
 }
 
 static bool tc_shape_ok(const pb_chain *c, const Segment &s)
 {
     if (c->dtype != PB_F32 || (c->flags & PB_CHAIN_NO_TENSOR) || c->C % kTcCh != 0) return false;
+    if (c->C / kTcCh > c->num_sms) return false;  // a CTA never owns two tiles of the last time step (chain_tc.cuh, carried state)
     if (s.fir_stage < 0 || s.bq_stage < 0 || s.rs_stage < 0) return false;
     if (s.Hf + 1 > kTcMaxTaps || s.Hf < 1) return false;
     return s.up == kTcUp && s.down == kTcFrames && s.P == kTcP;
 }
 
-// One K2 launch: `n` (a multiple of 160) input frames of segment `s`.
+// per-launch switches of the K2 function attributes (per device, set once)
+static int32_t tc_configure_once(int device)
+{
+    static std::once_flag once[64];
+    static cudaError_t err[64];
+    if (device < 0 || device >= 64) return fail(PB_ERR_INVALID, "device ordinal %d", device);
+    std::call_once(once[device], [&] {
+        err[device] = cudaFuncSetAttribute(chain_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+        if (err[device] == cudaSuccess)
+            err[device] = cudaFuncSetAttribute(chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+        if (err[device] == cudaSuccess)
+            err[device] = cudaFuncSetAttribute(chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    });
+    PB_CUDA(err[device]);
+    return PB_OK;
+}
+
+static int32_t tc_reset_scales(pb_chain *c, Segment &s, cudaStream_t stream)
+{
+    // before the first call nothing is known about the levels: assume full scale (|g x| = 1); pass B corrects it
+    std::vector<float> init((size_t)4 * c->C);
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < c->C; i++) {
+            init[(size_t)(2 * k) * c->C + i] = kSigTarget;
+            init[(size_t)(2 * k + 1) * c->C + i] = 1.0f / kSigTarget;
+        }
+    PB_CUDA(cudaMemcpyAsync(s.d_tc_scale, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemsetAsync(s.d_tc_peak, 0, sizeof(unsigned) * 2 * (size_t)c->C, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));  // `init` is pageable host memory
+    s.tc_k = 0;
+    return PB_OK;
+}
+
+// One K2 call: `n` (a multiple of 160) input frames of segment `s`, as two launches of the same kernel: pass A with the scales the
+// previous call ended with, pass B which verifies them and returns at once unless a channel left its grid window (chain_tc.cuh).
 static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_t n, void *out, bool is_last_segment,
                                  cudaStream_t stream)
 {
-    static bool attr_set[64] = {false};  // function attributes are per device
-    if (c->device < 0 || c->device >= 64 || !attr_set[c->device]) {
-        PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        PB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        if (c->device >= 0 && c->device < 64) attr_set[c->device] = true;
-    }
-    TcParams p{};
-    int32_t r = make_frame_map(&p.tm_in, in, c->C, n);
+    int32_t r = tc_configure_once(c->device);
     if (r != PB_OK) return r;
-    r = make_frame_map(&p.tm_hist, s.d_xhist[s.pp], c->C, s.Hf);
+    TcParams p{};
+    r = cached_frame_map(c, &p.tm_in, in, n);
+    if (r != PB_OK) return r;
+    r = cached_frame_map(c, &p.tm_hist, s.d_xhist[s.pp], s.Hf);
     if (r != PB_OK) return r;
     p.out = (float *)out;
     p.tables = (const __half *)s.d_tc_tables;
@@ -520,24 +589,21 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     p.lb_inc = (double *)s.d_inc;
     p.lb_status = s.d_status;
     const bool meter = is_last_segment && (c->flags & PB_CHAIN_METER);
-    p.meter_peak = meter ? c->d_meter : nullptr;
-    p.meter_sumsq = meter ? c->d_meter + c->C : nullptr;
+    p.meter_main = meter ? c->d_meter : nullptr;
+    p.meter_scratch = meter ? c->d_meter_scratch : nullptr;
+    p.scale = s.d_tc_scale + (size_t)s.tc_k * 2 * c->C;
+    p.scale_next = s.d_tc_scale + (size_t)(s.tc_k ^ 1) * 2 * c->C;
+    p.peak = s.d_tc_peak + (size_t)s.tc_k * c->C;
+    p.peak_next = s.d_tc_peak + (size_t)(s.tc_k ^ 1) * c->C;
     p.err_flag = reinterpret_cast<int *>(c->d_ticket + 1);
     p.C = c->C;
     p.n_tiles = (int)(n / kTcFrames);
     p.n_cg = c->C / kTcCh;
     p.hist_rows = s.Hf;
-    c->epoch = (c->epoch % 0x3ffffffeu) + 1u;
-    p.epoch = c->epoch;
-    const double sx = 2048.0;
-    p.scale_in = (float)(s.g[0] * sx);
-    p.scale_hist = (float)sx;
-    p.inv_scale_in = (float)(1.0 / sx);
-    const double sf = 2048.0;  // grid of the FIR output pieces (values beyond +-1 keep an exact remainder, see ep_block)
-    p.fscale = (float)(s.g[1] * sf / (sx * std::ldexp(1.0, s.tc_sh)));
-    p.inv_fgrid = (float)(1.0 / sf);
-    p.yh_scale = (float)(sf / s.g[2]);
-    p.descale_rs = (float)(s.g[2] * s.g[3] / (sf * std::ldexp(1.0, s.tc_sh2)));
+    p.g_load = (float)s.g[0];
+    p.fscale = (float)(s.g[1] / std::ldexp(1.0, s.tc_sh));
+    p.inv_gbq = (float)(1.0 / s.g[2]);
+    p.descale_rs = (float)(s.g[2] * s.g[3] / std::ldexp(1.0, s.tc_sh2));
     p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
     p.g_bq = s.g[2];
     for (int i = 0; i < 4; i++) {
@@ -559,7 +625,8 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     const int total = p.n_tiles * p.n_cg;
     const int grid = std::min(total, c->num_sms);
     // development aid: PB_TC_PROF=1 prints per-role cycle counters (averaged over CTAs) for every K2 launch
-    static const bool prof_on = getenv("PB_TC_PROF") != nullptr;
+    static const int prof_mode = getenv("PB_TC_PROF") ? atoi(getenv("PB_TC_PROF")) : 0;   // 1: counters, 2: timeline of CTA 0
+    const bool prof_on = prof_mode != 0;
     static const int dbg = getenv("PB_TC_DBG") ? atoi(getenv("PB_TC_DBG")) : 0;
     p.dbg = dbg;
     long long *d_prof = nullptr;
@@ -567,34 +634,61 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         PB_CUDA(cudaMalloc((void **)&d_prof, sizeof(long long) * tc::kProfCount * grid));
         PB_CUDA(cudaMemset(d_prof, 0, sizeof(long long) * tc::kProfCount * grid));
         p.prof = d_prof;
+        PB_CUDA(cudaMalloc((void **)&p.trace, sizeof(long long) * tc::kTraceTiles * tc::kTraceRoles * 32));
+        PB_CUDA(cudaMemset(p.trace, 0, sizeof(long long) * tc::kTraceTiles * tc::kTraceRoles * 32));
     }
-    if (prof_on) chain_tc_kernel<true><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
-    else chain_tc_kernel<false><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
-    PB_CUDA(cudaGetLastError());
+    for (int pass = 0; pass < 2; pass++) {
+        p.pass = pass;
+        // the two passes publish their look-back states under different epochs; pass A meters into the scratch copy
+        c->epoch = (c->epoch % 0x3ffffffeu) + 1u;
+        p.epoch = c->epoch;
+        double *mtr = !meter ? nullptr : pass == 0 ? c->d_meter_scratch : c->d_meter;
+        p.meter_peak = mtr;
+        p.meter_sumsq = mtr ? mtr + c->C : nullptr;
+        if (prof_mode == 1) chain_tc_kernel<1><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+        else if (prof_mode == 2) chain_tc_kernel<2><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+        else chain_tc_kernel<0><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+        PB_CUDA(cudaGetLastError());
+        c->launches++;
+        if (prof_on && pass == 0) {
+            PB_CUDA(cudaStreamSynchronize(stream));
+            std::vector<long long> h((size_t)tc::kProfCount * grid);
+            PB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            static const char *names[] = {"prod_wait_empty", "mma_wait_tmem", "mma_wait_cvt", "mma_issue", "cvt_wait_raw",
+                                          "cvt_wait_a1", "cvt_work", "drain_wait_blk", "drain_work", "drain_lookback", "total",
+                                          "out_wait", "out_main", "mma2_wait_a2", "out_tmem_ld", "out_math", "ns (MMA1 warp)", "-"};
+            const double tiles_per_cta = (double)total / grid;
+            fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
+            for (int k = 0; k < tc::kProfCount; k++) {
+                double sum = 0;
+                for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + k];
+                fprintf(stderr, "  %-16s %10.0f\n", names[k], sum / grid / tiles_per_cta);
+            }
+            PB_CUDA(cudaMemset(d_prof, 0, sizeof(long long) * tc::kProfCount * grid));
+            // event timeline of CTA 0 (clock64, relative to the first event)
+            std::vector<long long> tr((size_t)tc::kTraceTiles * tc::kTraceRoles * 32);
+            PB_CUDA(cudaMemcpy(tr.data(), p.trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            long long t0 = 0;
+            for (long long v : tr)
+                if (v && (!t0 || v < t0)) t0 = v;
+            static const char *roles[] = {"mma1", "cvt0", "cvt1", "drainA", "drainB", "mma2", "out"};
+            for (int ti = 0; ti < tc::kTraceTiles; ti++)
+                for (int r = 0; r < tc::kTraceRoles; r++) {
+                    fprintf(stderr, "[PB_TC_TRACE] tile %d %-6s", ti, roles[r]);
+                    for (int k = 0; k < 32; k++) {
+                        const long long v = tr[((size_t)ti * tc::kTraceRoles + r) * 32 + k];
+                        if (v) fprintf(stderr, " %d:%lld", k, v - t0);
+                    }
+                    fprintf(stderr, "\n");
+                }
+        }
+    }
     if (prof_on) {
         PB_CUDA(cudaStreamSynchronize(stream));
-        std::vector<long long> h((size_t)tc::kProfCount * grid);
-        PB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_prof);
-        static const char *names[] = {"prod_wait_empty", "mma_wait_tmem", "mma_wait_cvt", "mma_issue", "cvt_wait_raw",
-                                      "cvt_wait_cvt", "cvt_work", "drain_wait_blk", "drain_work", "drain_lookback", "total",
-                                      "out_wait", "out_main", "mma2_wait_a2"};
-        const double tiles_per_cta = (double)total / grid;
-        fprintf(stderr, "[PB_TC_PROF] grid %d, %.1f tiles/CTA; cycles per tile (mean over CTAs):\n", grid, tiles_per_cta);
-        fprintf(stderr, "  out: group_sync, mailbox+states, tmem ld, outputs (then unused):");
-        for (int q = 0; q < kTcChunks; q++) {
-            double sum = 0;
-            for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + tc::kProfChunk0 + q];
-            fprintf(stderr, " %.0f", sum / grid / tiles_per_cta);
-        }
-        fprintf(stderr, "\n");
-        for (int k = 0; k <= tc::kProfMma2Wait; k++) {
-            double sum = 0;
-            for (int b = 0; b < grid; b++) sum += (double)h[(size_t)b * tc::kProfCount + k];
-            fprintf(stderr, "  %-16s %10.0f\n", names[k], sum / grid / tiles_per_cta);
-        }
+        cudaFree(p.trace);
     }
-    c->launches++;
+    s.tc_k ^= 1;
     s.pp ^= 1;
     return PB_OK;
 }
@@ -759,6 +853,12 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     s.tc_ok = tc_shape_ok(c, s);
     if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_tables, (size_t)TcTables::kBytes));
     if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_rc, (size_t)kTcRcRows * 8 * sizeof(float)));
+    if (s.tc_ok) {
+        PB_CUDA(cudaMalloc((void **)&s.d_tc_scale, sizeof(float) * 4 * (size_t)c->C));
+        PB_CUDA(cudaMalloc((void **)&s.d_tc_peak, sizeof(unsigned) * 2 * (size_t)c->C));
+        int32_t r = tc_reset_scales(c, s, c->st_compute);
+        if (r != PB_OK) return r;
+    }
     return refresh_segment_params(c, s);
 }
 
@@ -771,6 +871,7 @@ static int32_t reset_segment(pb_chain *c, Segment &s)
         if (s.d_state[i]) PB_CUDA(cudaMemsetAsync(s.d_state[i], 0, sizeof(double) * (size_t)c->C * 2, c->st_compute));
     }
     s.acc = 0;
+    if (s.tc_ok) return tc_reset_scales(c, s, c->st_compute);
     return PB_OK;
 }
 
@@ -961,7 +1062,9 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
             // of 160.  A call that does not start or end there (a 4096-frame buffer never does both) is cut into a head up to the
             // next such position, the aligned middle and a tail; head and tail go through K1, which shares every piece of
             // carried state with K2 (launches on one stream are ordered like separate calls).
-            const bool tc_eligible = s.tc_ok && s.g[2] != 0.0 && s.tc_level_ok && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
+            // (the f pieces of MMA2 are fp16: the FIR output of a channel at its grid peak, |g_fir| sum|h| * 2047, must stay inside)
+            const bool tc_eligible = s.tc_ok && s.g[2] != 0.0 && s.g[0] != 0.0 && s.tc_level_ok && std::fabs(s.g[1]) * s.tc_fir_l1 <= 28.0 &&
+                                     ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
             int64_t head = 0;
             if (tc_eligible)
                 while (head < s.down && (s.acc + head * s.up) % s.down != 0) head++;
@@ -1030,6 +1133,7 @@ extern "C" int32_t pb_chain_destroy(pb_chain *c)
     }
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_meter) cudaFree(c->d_meter);
+    if (c->d_meter_scratch) cudaFree(c->d_meter_scratch);
     if (c->st_compute) cudaStreamDestroy(c->st_compute);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
@@ -1111,6 +1215,8 @@ extern "C" int32_t pb_chain_create(const pb_chain_desc *desc, pb_chain **out)
     if (c->flags & PB_CHAIN_METER) {
         PB_TRY_CUDA(cudaMalloc((void **)&c->d_meter, sizeof(double) * 2 * (size_t)c->C));
         PB_TRY_CUDA(cudaMemset(c->d_meter, 0, sizeof(double) * 2 * (size_t)c->C));
+        PB_TRY_CUDA(cudaMalloc((void **)&c->d_meter_scratch, sizeof(double) * 2 * (size_t)c->C));
+        PB_TRY_CUDA(cudaMemset(c->d_meter_scratch, 0, sizeof(double) * 2 * (size_t)c->C));
     }
     plan_segments(c);
     double rate = c->sample_rate;
@@ -1140,6 +1246,9 @@ extern "C" int32_t pb_chain_reset(pb_chain *c)
         if (r != PB_OK) return r;
     }
     if (c->d_meter) PB_CUDA(cudaMemsetAsync(c->d_meter, 0, sizeof(double) * 2 * (size_t)c->C, c->st_compute));
+    if (c->d_meter_scratch) PB_CUDA(cudaMemsetAsync(c->d_meter_scratch, 0, sizeof(double) * 2 * (size_t)c->C, c->st_compute));
+    // a look-back timeout (the only kernel-side error) is not sticky: a reset chain starts clean
+    PB_CUDA(cudaMemsetAsync(c->d_ticket + 1, 0, sizeof(unsigned long long), c->st_compute));
     c->meter_frames = 0;
     PB_CUDA(cudaStreamSynchronize(c->st_compute));
     return PB_OK;
@@ -1175,6 +1284,18 @@ extern "C" int32_t pb_chain_process_batch_device(pb_chain *c, const void *in_dev
                             (cudaStream_t)stream);
 }
 
+// The only kernel-side failure left is a look-back wait that ran into its bound (a tile's predecessors were not scheduled
+// for ~0.3 s: the device is shared with something that holds its SMs).  It is reported once and cleared, so the chain can be
+// reset and used again; what the affected call wrote is undefined.
+static int32_t take_kernel_error(pb_chain *c)
+{
+    int flag = 0;
+    PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!flag) return PB_OK;
+    PB_CUDA(cudaMemset(c->d_ticket + 1, 0, sizeof(unsigned long long)));
+    return fail(PB_ERR_CUDA, "fused kernel: look-back wait timed out (kernel error flag %d); the carried state is undefined, call pb_chain_reset", flag);
+}
+
 extern "C" int32_t pb_chain_sync(pb_chain *c, void *stream)
 {
     if (!c) return fail(PB_ERR_INVALID, "pb_chain_sync: NULL chain");
@@ -1182,11 +1303,7 @@ extern "C" int32_t pb_chain_sync(pb_chain *c, void *stream)
     PB_CUDA(dg.err);
     PB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     PB_CUDA(cudaStreamSynchronize(c->st_compute));
-    int flag = 0;
-    PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fixed-point range of the fp16 split (|g*x| > 1, or |y| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
-                                                    : "fused kernel: look-back wait timed out (kernel error flag set)");
-    return PB_OK;
+    return take_kernel_error(c);
 }
 
 static int32_t ensure_slot(pb_chain *c, Slot &sl)
@@ -1223,9 +1340,19 @@ extern "C" int32_t pb_chain_submit(pb_chain *c, const void *in_host, const int64
     Slot &sl = c->slots[c->slot_head];
     int32_t r = ensure_slot(c, sl);
     if (r != PB_OK) return r;
-    int64_t tin = 0;
-    for (int i = 0; i < n_buffers; i++) tin += buf_frames[i] > 0 ? buf_frames[i] : 0;
+    // validate the whole call before anything is enqueued: a rejected call must leave the carried state untouched
+    if (n_buffers > c->max_batch) return fail(PB_ERR_CAPACITY, "pb_chain_submit: %d buffers > max_batch %d", n_buffers, c->max_batch);
+    for (int i = 0; i < n_buffers; i++) {
+        if (buf_frames[i] < 0 || buf_frames[i] > c->buffer_frames)
+            return fail(PB_ERR_INVALID, "pb_chain_submit: buffer %d has %lld frames (bufferSize %d)", i, (long long)buf_frames[i], c->buffer_frames);
+        if (i + 1 < n_buffers && buf_frames[i] != c->buffer_frames)
+            return fail(PB_ERR_INVALID, "pb_chain_submit: only the last buffer of a batch may be short");
+    }
+    int64_t tin = 0, tout_need = 0;
+    count_outputs(c, buf_frames, n_buffers, nullptr, &tin, &tout_need, false);
     if (tin > c->max_frames) return fail(PB_ERR_CAPACITY, "pb_chain_submit: %lld frames > buffer_frames*max_batch", (long long)tin);
+    if (tout_need > out_capacity_frames)
+        return fail(PB_ERR_CAPACITY, "pb_chain_submit: output needs %lld frames, capacity %lld", (long long)tout_need, (long long)out_capacity_frames);
     const size_t in_bytes = c->elem * (size_t)tin * c->C;
     if (tin > 0 && (!in_host || !out_host)) return fail(PB_ERR_INVALID, "pb_chain_submit: NULL buffer");
     // H2D: pinned caller memory goes direct, pageable memory (the Go heap) is
@@ -1248,7 +1375,6 @@ extern "C" int32_t pb_chain_submit(pb_chain *c, const void *in_host, const int64
     if (r != PB_OK) return r;
     int64_t tout = 0;
     for (auto v : sl.out_counts) tout += v;
-    if (tout > out_capacity_frames) return fail(PB_ERR_CAPACITY, "pb_chain_submit: output needs %lld frames", (long long)tout);
     PB_CUDA(cudaEventRecord(sl.ev_done, c->st_compute));
     PB_CUDA(cudaStreamWaitEvent(c->st_d2h, sl.ev_done, 0));
     sl.out_frames = tout;
@@ -1279,20 +1405,18 @@ extern "C" int32_t pb_chain_collect(pb_chain *c, int64_t *buf_out_frames, int32_
     Slot &sl = c->slots[c->slot_tail];
     if (n_buffers != (int)sl.out_counts.size()) return fail(PB_ERR_INVALID, "pb_chain_collect: batch had %zu buffers", sl.out_counts.size());
     PB_CUDA(cudaEventSynchronize(sl.ev_d2h));
-    {
-        int flag = 0;
-        PB_CUDA(cudaMemcpy(&flag, c->d_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost));
-        if (flag) return fail(PB_ERR_CUDA, flag == 2 ? "tensor path: input exceeds the fixed-point range of the fp16 split (|g*x| > 1, or |y| > 29); recreate the chain with PB_CHAIN_NO_TENSOR"
-                                                        : "fused kernel: look-back wait timed out (kernel error flag set)");
+    const int32_t kerr = take_kernel_error(c);
+    if (kerr == PB_OK) {
+        if (sl.user_out && sl.out_frames) memcpy(sl.user_out, sl.h_out, c->elem * (size_t)sl.out_frames * c->C);
+        if (buf_out_frames)
+            for (int i = 0; i < n_buffers; i++) buf_out_frames[i] = sl.out_counts[(size_t)i];
     }
-    if (sl.user_out && sl.out_frames) memcpy(sl.user_out, sl.h_out, c->elem * (size_t)sl.out_frames * c->C);
-    if (buf_out_frames)
-        for (int i = 0; i < n_buffers; i++) buf_out_frames[i] = sl.out_counts[(size_t)i];
+    // the slot is released whether or not the batch succeeded: a failed batch must not wedge the pipeline
     sl.busy = false;
     sl.user_out = nullptr;
     c->slot_tail ^= 1;
     c->slots_busy--;
-    return PB_OK;
+    return kerr;
 }
 
 extern "C" int32_t pb_chain_process(pb_chain *c, const void *in_host, int64_t in_frames, void *out_host,
