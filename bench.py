@@ -145,6 +145,48 @@ def cpu_chain_throughput(n_buffers: int, threads: int, repeats: int = 1):
     return repeats * n_buffers * BUFFER_FRAMES * CHANNELS / dt / 1e6, dt
 
 
+def cpu_thread_per_stage(n_buffers: int):
+    """The reference's own execution shape (run.go:173-196 + fitting.Async, fitting.go:56-60): one thread per component,
+    cap-1 queues between them, every Processor a single-threaded float64 loop (the C restatement, one stage per chain).
+    The oracle calls release the GIL, so the stage threads really overlap.  Returns Msamples/s."""
+    import queue
+
+    import _oracle as orc
+    from pipe_b200 import design
+    stages = design.config_stages("chain4")
+    procs = [orc.Chain(CHANNELS, [st]) for st in stages]
+    x = orc.source_fill(0, BUFFER_FRAMES * CHANNELS).reshape(BUFFER_FRAMES, CHANNELS)
+    qs = [queue.Queue(maxsize=1) for _ in range(len(procs) + 1)]
+
+    def source():
+        for _ in range(n_buffers):
+            qs[0].put(x)
+        qs[0].put(None)
+
+    def processor(i):
+        while True:
+            buf = qs[i].get()
+            if buf is None:
+                qs[i + 1].put(None)
+                return
+            qs[i + 1].put(procs[i].process(buf))
+
+    threads = [threading.Thread(target=source)] + [threading.Thread(target=processor, args=(i,)) for i in range(len(procs))]
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    frames_out = 0
+    while True:  # the Sink
+        buf = qs[-1].get()
+        if buf is None:
+            break
+        frames_out += len(buf)
+    dt = time.perf_counter() - t0
+    for t in threads:
+        t.join()
+    return n_buffers * BUFFER_FRAMES * CHANNELS / dt / 1e6, dt, len(threads) + 1
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -221,6 +263,196 @@ def hbm_bound_runs(local, stream):
     return out
 
 
+def pin_to_gpu_numa_node(local: int) -> str:
+    """Pin this rank's host threads (and therefore the pages of the pinned staging it allocates next) to the CPUs NVML
+    reports as local to its GPU.  Eight ranks staging 640 MB per step each through one NUMA node was the e2e scaling limit."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"NVML-local CPUs ({len(cpus)} of {os.cpu_count()})"
+        return "NVML reported no local CPUs inside this cgroup: unchanged"
+    except Exception as e:  # no NVML, no permission: report and carry on
+        return f"unchanged ({type(e).__name__})"
+
+
+def pcie_ceiling(nbytes: int, barrier):
+    """Pinned H2D and D2H copies of the e2e batch size running at the same time on two streams: the box's ceiling for the
+    pipelined host path, measured on every rank at once.  Returns GB/s per direction."""
+    import torch
+    n = nbytes // 4
+    h_in, h_out = torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.float32, device="cuda"), torch.empty(n, dtype=torch.float32, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * n * 4 / (time.perf_counter() - t0) / 1e9
+    run(1)
+    barrier()
+    return run(4)
+
+
+def dropin_e2e(local: int, n_buffers: int = 12):
+    """The drop-in case, shaped like the cgo shim (go/pipeb200.go): the pipe hands over ONE pageable float64 buffer per
+    ProcessFunc call (pipe.go:394,437,438); the shim marshals it into its staging (ReadFloat64, converting to float32 in
+    float32 mode), calls pb_chain_process (H2D, kernels, D2H, synchronous) and marshals the result back (WriteFloat64).
+    Both compute modes, timed on the host clock around the whole call sequence."""
+    from pipe_b200 import abi, design
+    import _oracle as orc  # input generation only (outside the timed region)
+    x64 = orc.source_fill(0, BUFFER_FRAMES * CHANNELS).reshape(BUFFER_FRAMES, CHANNELS)   # pageable float64, as signal.Floating
+    out64 = np.empty_like(x64)
+    res = {}
+    for mode, dt in (("float64 compute (go: Chain)", np.float64), ("float32 compute (go: ChainWith{Float32: true})", np.float32)):
+        chain = abi.Chain(CHANNELS, design.config_stages("chain4"), buffer_frames=BUFFER_FRAMES, dtype=dt, device=local)
+        pin_in = abi.PinnedBuffer(x64.size * np.dtype(dt).itemsize)
+        pin_out = abi.PinnedBuffer(x64.size * np.dtype(dt).itemsize)
+        a_in, a_out = pin_in.array(x64.shape, dt), pin_out.array(x64.shape, dt)
+        got = abi._i64()
+        lib = abi.lib()
+
+        def one():
+            np.copyto(a_in, x64, casting="same_kind")            # ReadFloat64 (+ narrowing in float32 mode)
+            abi.check(lib.pb_chain_process(chain._h, pin_in.ptr, BUFFER_FRAMES, pin_out.ptr, BUFFER_FRAMES, abi.C.byref(got)))
+            n = got.value
+            np.copyto(out64[:n], a_out[:n])                       # WriteFloat64 (+ widening)
+            return n
+        for _ in range(3):
+            one()
+        t0 = time.perf_counter()
+        for _ in range(n_buffers):
+            n = one()
+        dt_s = time.perf_counter() - t0
+        res[mode] = {"value": n_buffers * BUFFER_FRAMES * CHANNELS / dt_s / 1e6, "unit": "Msamples/s",
+                     "ms_per_buffer": 1e3 * dt_s / n_buffers, "kernel_path": chain.last_path()[0], "out_frames_last": int(n)}
+        chain.close()
+        pin_in.free()
+        pin_out.free()
+    return res
+
+
+def per_buffer_run(local: int, stream, n_buffers: int = 40):
+    """One 4096 x 1024 buffer per pb_chain_process_batch_device call, device-resident: the reference's ProcessFunc granularity
+    (pipe.go:438) without the host copies."""
+    import torch
+    from pipe_b200 import abi, design
+    peak, _ = measured_peak()
+    chain = abi.Chain(CHANNELS, design.config_stages("chain4"), buffer_frames=BUFFER_FRAMES, device=local)
+    x = torch.empty((BUFFER_FRAMES * n_buffers, CHANNELS), dtype=torch.float32, device=f"cuda:{local}")
+    y = torch.empty((BUFFER_FRAMES, CHANNELS), dtype=torch.float32, device=f"cuda:{local}")
+    abi.source_fill(x.data_ptr(), abi.PB_F32, 0, x.numel(), seed=1234, device=local)
+    step = BUFFER_FRAMES * CHANNELS * 4
+    _, l0 = chain.last_path()
+    for b in range(5):
+        chain.process_batch_device(x.data_ptr() + b * step, [BUFFER_FRAMES], y.data_ptr(), BUFFER_FRAMES, stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    _, l1 = chain.last_path()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for b in range(5, n_buffers):
+        chain.process_batch_device(x.data_ptr() + b * step, [BUFFER_FRAMES], y.data_ptr(), BUFFER_FRAMES, stream=stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    chain.sync(stream.cuda_stream)
+    ms = e0.elapsed_time(e1) / (n_buffers - 5)
+    gbs = BUFFER_FRAMES * CHANNELS * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9
+    out = {"workload": "configs[2], ONE 4096 x 1024 buffer per call (device-resident; the reference's ProcessFunc granularity)",
+           "value": BUFFER_FRAMES * CHANNELS / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "us_per_buffer": 1e3 * ms,
+           "launches_per_call": (l1 - l0) / 5.0, "kernel_path": chain.last_path()[0],
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}}
+    chain.close()
+    return out
+
+
+def fan_in_run(rank, local, world, stream):
+    """configs[4]: `world` Lines x 256 ch, each through the 4-stage chain on its own GPU, then the fan-in sum onto rank 0 --
+    once as an NCCL reduce, once as ONE mixer kernel on rank 0 that pulls the peers' buffers over NVLink while it sums
+    (pb_mix_sum_device on pb_ipc_open'ed pointers).  Device-timed on rank 0; checked against the oracle's sum."""
+    import torch
+    import torch.distributed as dist
+    from pipe_b200 import abi, design, shard
+    ch, bf, nb = 256, 4000, 4        # 4000 = 25 tiles of 160 frames
+    frames = bf * nb
+    dev = torch.device("cuda", local)
+    stages = design.config_stages("chain4")
+    chain = abi.Chain(ch, stages, buffer_frames=bf, max_batch=nb, device=local)
+    x = torch.empty((frames, ch), dtype=torch.float32, device=dev)
+    y = torch.zeros((frames, ch), dtype=torch.float32, device=dev)
+    abi.source_fill(x.data_ptr(), abi.PB_F32, 0, frames * ch, seed=1234, line=rank, device=local)
+    sptr = stream.cuda_stream
+    counts = chain.process_batch_device(x.data_ptr(), [bf] * nb, y.data_ptr(), frames, stream=sptr)
+    chain.sync(sptr)
+    n_out = sum(counts)
+    mine = y[:n_out].clone()
+    reps = 10
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        return e0.elapsed_time(e1) / reps
+    red = mine.clone()
+    shard.fan_in_reduce(red, dst=0)                    # result kept for the parity check (and warm-up)
+    scratch = mine.clone()
+    ms_nccl = timed(lambda: dist.reduce(scratch, dst=0))   # accumulates on rank 0; only the time matters here
+    out = torch.zeros_like(mine)
+    pf = shard.PeerFanIn(mine.data_ptr(), mine.numel(), abi.PB_F32, local, dst=0)
+    pf.sum_into(out.data_ptr(), stream=sptr)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_peer = None
+    if rank == 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            abi.mix_sum(pf.peer_ptrs, abi.PB_F32, mine.numel(), out.data_ptr(), device=local, stream=sptr)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_peer = e0.elapsed_time(e1) / reps
+    dist.barrier()
+    pf.close()
+    res = None
+    if rank == 0:
+        import _oracle as orc
+        ref = None
+        for line in range(world):
+            cpu = orc.Chain(ch, stages)
+            xs = orc.source_fill(0, frames * ch, line=line).reshape(frames, ch)
+            r = np.concatenate([cpu.process(xs[i * bf:(i + 1) * bf], threads=os.cpu_count() or 1) for i in range(nb)])
+            ref = r if ref is None else ref + r
+        pk = np.abs(ref).max(axis=0)
+        line_mb = mine.numel() * 4 / 1e6
+        res = {"workload": f"configs[4]: {world} Lines x {ch} ch -> [4-stage chain] -> fan-in sum on rank 0",
+               "frames_out": int(n_out), "bytes_per_line": mine.numel() * 4,
+               "nvlink_bytes_algorithmic": (world - 1) * mine.numel() * 4,
+               "nccl_reduce": {"ms": ms_nccl, "err_over_peak": float((np.abs(red.cpu().numpy() - ref).max(axis=0) / pk).max()),
+                               "gbs_into_rank0": (world - 1) * line_mb / ms_nccl},
+               "peer_mixer_kernel": {"ms": ms_peer, "err_over_peak": float((np.abs(out.cpu().numpy() - ref).max(axis=0) / pk).max()),
+                                     "gbs_into_rank0": (world - 1) * line_mb / ms_peer,
+                                     "note": "one pb_mix_sum_device launch on rank 0: loads of the 3 peers' buffers over NVLink + sum + store"}}
+    chain.close()
+    return res
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -232,6 +464,7 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; pipe_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa_node(local)      # before any pinned staging is allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -298,6 +531,7 @@ def run_cuda(args):
         return oc
 
     e2e_run(2)  # warm: allocates the slots
+    pcie_gbs = pcie_ceiling(frames * CHANNELS * 4, barrier)   # every rank at once: the box's ceiling at this N
     barrier()
     t0 = time.perf_counter()
     oc = e2e_run(e2e_steps)
@@ -305,15 +539,24 @@ def run_cuda(args):
     e2e_s = time.perf_counter() - t0
     result_probe = float(pin_out[(e2e_steps - 1) & 1][0, 0])  # device->host result actually read
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_s * 1e3, -pcie_gbs], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
+        total_ms, e2e_ms, pcie_min = float(t[0]), float(t[1]), -float(t[2])
+        t = torch.tensor([pcie_gbs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        pcie_sum = float(t[0])
     else:
-        e2e_ms = e2e_s * 1e3
+        e2e_ms, pcie_min, pcie_sum = e2e_s * 1e3, pcie_gbs, pcie_gbs
+    # a step moves 4 B per sample in and 4*147/160 B out at the same time: the input direction is the longer one
+    e2e_ceiling = world * pcie_min * 1e9 / 4.0 / 1e6
+    fan_in = fan_in_run(rank, local, world, stream) if (world == 4 and not args.no_secondary) else None
 
     # ---- the HBM-bound runs (configs[1] and the same run at 1024 ch) on the streaming kernels, device-resident; reported
     #      beside the headline so that every BASELINE.json config that fits one GPU has a measured roofline fraction
     secondary = hbm_bound_runs(local, stream) if (rank == 0 and world == 1 and not args.no_secondary) else None
+    if secondary is not None:
+        secondary.append(per_buffer_run(local, stream))
+    dropin = dropin_e2e(local) if (rank == 0 and world == 1 and not args.no_secondary) else None
 
     samples_step = frames * CHANNELS               # per rank
     value = world * samples_step * args.steps / (total_ms * 1e-3) / 1e6
@@ -326,6 +569,7 @@ def run_cuda(args):
         cpu_threads = os.cpu_count() or 1
         # the CPU baseline is timed at N = 1 only (the driver's scaling runs reuse that line)
         cpu_val, cpu_dt = cpu_chain_throughput(args.cpu_buffers, cpu_threads) if world == 1 else (None, 0.0)
+        tps = cpu_thread_per_stage(max(2, min(8, args.cpu_buffers // 8))) if (world == 1 and args.cpu_buffers >= 16) else None
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -346,16 +590,29 @@ def run_cuda(args):
             "cpu_baseline": {"value": cpu_val, "unit": "Msamples/s", "cores": cpu_threads, "kind": "port",
                              "sample": (f"{args.cpu_buffers} buffers of {BUFFER_FRAMES}x{CHANNELS} float64 through the "
                                         f"C restatement (oracle/pipe_oracle.c), {cpu_threads} threads, {cpu_dt:.1f} s")
-                             if world == 1 else "not timed at N > 1: the CPU baseline is measured by the N = 1 run"},
+                             if world == 1 else "not timed at N > 1: the CPU baseline is measured by the N = 1 run",
+                             "thread_per_stage": ({"value": tps[0], "unit": "Msamples/s", "threads": tps[2], "seconds": tps[1],
+                                                   "note": "the reference's own shape: one thread per component, cap-1 queues "
+                                                           "(run.go:173-196, fitting.go:56-60), each Processor a single-threaded "
+                                                           "float64 loop; the channel-split number above is the faster, conservative baseline"}
+                                                  if tps else None)},
             "e2e": {"value": e2e_value, "unit": "Msamples/s",
                     "h2d_bytes_per_step": frames * CHANNELS * 4, "d2h_bytes_per_step": out_frames * CHANNELS * 4,
-                    "steps": e2e_steps, "path": "pb_chain_submit/collect, pinned host buffers, 2 batches in flight",
-                    "result_probe": result_probe},
+                    "steps": e2e_steps, "path": "pb_chain_submit/collect, PINNED float32 host buffers, batches of "
+                                                f"{nb} buffers, 2 batches in flight (the best case for a host path, not the drop-in case: see dropin)",
+                    "result_probe": result_probe, "cpu_affinity": affinity,
+                    "pcie_ceiling": {"gbs_per_direction_per_rank_min": pcie_min, "gbs_per_direction_all_ranks": pcie_sum,
+                                     "msamples_per_s_all_ranks": e2e_ceiling, "frac_of_ceiling": e2e_value / e2e_ceiling,
+                                     "how": "pinned H2D + D2H copies of the batch size on two streams, all ranks at once, "
+                                            "inside this run"},
+                    "dropin": dropin},
             "gpu_launches": int(launches1 - launches0),
             "clocks": clk,
         }
         if secondary is not None:
             line["secondary"] = secondary
+        if fan_in is not None:
+            line["fan_in"] = fan_in
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

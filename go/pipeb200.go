@@ -1,7 +1,7 @@
 // Package pipeb200 puts a fused CUDA chain (libpipe_b200.so, include/pipe_b200.h) behind
 // pipelined/pipe's Processor plugin boundary.
 //
-// STATUS: UNCOMPILED AND UNTESTED.  The build image has no Go toolchain and no copy of
+// STATUS: UNCOMPILED AND UNTESTED (round 2: float32-compute mode, restart-safe lifecycle, per-call error text).  The build image has no Go toolchain and no copy of
 // pipelined.dev/signal v0.10.0, so this file has never been through `go build`.  It is the
 // binding a pipe maintainer would add; the same C-ABI is exercised from Python (ctypes) and
 // C++ in this repository's tests.
@@ -56,12 +56,35 @@ func Resample(up, down int, proto []float64) Stage {
 	return Stage{kind: C.PB_STAGE_RESAMPLE, up: up, down: down, taps: proto}
 }
 
-func lastError(code C.int32_t) error {
-	return fmt.Errorf("pipe_b200 error %d: %s", int(code), C.GoString(C.pb_last_error()))
+// call runs one C-ABI call and, on failure, reads the thread-local pb_last_error() on the SAME OS thread: goroutines migrate
+// between threads, so the message must be fetched before the goroutine can be rescheduled (ADVICE r1).
+func call(f func() C.int32_t) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := f(); rc != C.PB_OK {
+		return fmt.Errorf("pipe_b200 error %d: %s", int(rc), C.GoString(C.pb_last_error()))
+	}
+	return nil
 }
 
-// Chain returns the ProcessorAllocatorFunc (line.go:30) for a run of GPU stages on `device`.
+// Options of a fused chain.
+type Options struct {
+	Device int
+	// Float32 selects float32 arithmetic on the device.  pipe always hands over float64 buffers (pipe.go:394,437); with
+	// Float32 the marshalling copy converts on the way in and out.  This is what reaches the tcgen05 kernel (the 4-stage
+	// chain at channel counts that are multiples of 128) and the float32 streaming kernels; without it every chain runs
+	// the float64 kernels.  See INTEGRATION.md "which kernel a chain reaches".
+	Float32 bool
+	Flags   uint32 // PB_CHAIN_*
+}
+
+// Chain returns the ProcessorAllocatorFunc (line.go:30) for a run of GPU stages on `device`, float64 arithmetic.
 func Chain(device int, stages ...Stage) pipe.ProcessorAllocatorFunc {
+	return ChainWith(Options{Device: device}, stages...)
+}
+
+// ChainWith is Chain with options.
+func ChainWith(opt Options, stages ...Stage) pipe.ProcessorAllocatorFunc {
 	return func(mctx mutable.Context, bufferSize int, props pipe.SignalProperties) (pipe.Processor, error) {
 		// The descriptors (and the taps they point to) must live in C memory for the duration of
 		// pb_chain_create only: the library copies every coefficient and keeps no caller pointer.
@@ -90,14 +113,19 @@ func Chain(device int, stages ...Stage) pipe.ProcessorAllocatorFunc {
 				d.taps = (*C.double)(p)
 			}
 		}
+		dtype := C.int32_t(C.PB_F64)
+		if opt.Float32 {
+			dtype = C.PB_F32
+		}
 		desc := C.pb_chain_desc{
-			abi_version: C.PB_ABI_VERSION, device: C.int32_t(device), dtype: C.PB_F64, // pipe allocates Float64 (pipe.go:394,437)
+			abi_version: C.PB_ABI_VERSION, device: C.int32_t(opt.Device), dtype: dtype,
 			channels: C.int32_t(props.Channels), sample_rate: C.double(props.SampleRate),
-			buffer_frames: C.int32_t(bufferSize), max_batch: 1, n_stages: C.int32_t(len(stages)), stages: &cst[0],
+			buffer_frames: C.int32_t(bufferSize), max_batch: 1, n_stages: C.int32_t(len(stages)),
+			flags: C.int32_t(opt.Flags), stages: &cst[0],
 		}
 		var h *C.pb_chain
-		if rc := C.pb_chain_create(&desc, &h); rc != C.PB_OK {
-			return pipe.Processor{}, lastError(rc) // aborts binding, line.go:72-74
+		if err := call(func() C.int32_t { return C.pb_chain_create(&desc, &h) }); err != nil {
+			return pipe.Processor{}, err // aborts binding, line.go:72-74
 		}
 		var outCh C.int32_t
 		var outRate C.double
@@ -105,34 +133,87 @@ func Chain(device int, stages ...Stage) pipe.ProcessorAllocatorFunc {
 
 		// Staging in C memory: Go pointers must not be retained by C, and signal.Floating gives
 		// no access to its backing slice, so samples are marshalled through WriteFloat64/ReadFloat64
-		// (mock_test.go:120,128 show the same calls).
+		// (mock_test.go:120,128 show the same calls).  The staging is PINNED (pb_host_alloc_pinned): the library then
+		// copies straight from it instead of through its own pinned bounce buffer.
 		n := bufferSize * props.Channels
-		cin := (*[1 << 28]float64)(C.malloc(C.size_t(8 * n)))[:n:n]
-		cout := (*[1 << 28]float64)(C.malloc(C.size_t(8 * n)))[:n:n]
+		elem := 8
+		if opt.Float32 {
+			elem = 4
+		}
+		var pin, pout unsafe.Pointer
+		if err := call(func() C.int32_t { return C.pb_host_alloc_pinned(C.int64_t(n*elem), &pin) }); err != nil {
+			C.pb_chain_destroy(h)
+			return pipe.Processor{}, err
+		}
+		if err := call(func() C.int32_t { return C.pb_host_alloc_pinned(C.int64_t(n*elem), &pout) }); err != nil {
+			C.pb_host_free_pinned(pin)
+			C.pb_chain_destroy(h)
+			return pipe.Processor{}, err
+		}
+		in64 := (*[1 << 28]float64)(pin)[:n:n] // views of the same staging
+		out64 := (*[1 << 28]float64)(pout)[:n:n]
+		in32 := (*[1 << 29]float32)(pin)[:n:n]
+		out32 := (*[1 << 29]float32)(pout)[:n:n]
+		var tmp []float64 // float32 mode: ReadFloat64 / WriteFloat64 want []float64
+		if opt.Float32 {
+			tmp = make([]float64, n)
+		}
+		starts := 0
+
+		// The chain lives as long as the Processor: pipe binds components once (pipe.New) and a Pipe may be started again
+		// after Wait (TestReset, pipe_test.go:107-130).  The finalizer releases the device resources.
+		type owner struct{ h *C.pb_chain }
+		own := &owner{h}
+		runtime.SetFinalizer(own, func(o *owner) {
+			C.pb_chain_destroy(o.h)
+			C.pb_host_free_pinned(pin)
+			C.pb_host_free_pinned(pout)
+		})
 
 		return pipe.Processor{
 			SignalProperties: pipe.SignalProperties{Channels: int(outCh), SampleRate: signal.Frequency(outRate)},
+			StartFunc: func(context.Context) error { // a restarted Pipe begins from zero state
+				defer runtime.KeepAlive(own)
+				starts++
+				if starts == 1 {
+					return nil
+				}
+				return call(func() C.int32_t { return C.pb_chain_reset(h) })
+			},
 			ProcessFunc: func(in, out signal.Floating) (int, error) {
+				defer runtime.KeepAlive(own)
 				frames := in.Length()
-				signal.ReadFloat64(in, cin[:frames*props.Channels])
+				vals := frames * props.Channels
+				if opt.Float32 {
+					signal.ReadFloat64(in, tmp[:vals])
+					for i, v := range tmp[:vals] {
+						in32[i] = float32(v)
+					}
+				} else {
+					signal.ReadFloat64(in, in64[:vals])
+				}
 				var got C.int64_t
 				// goroutines migrate between OS threads; the library selects its device on every call
-				rc := C.pb_chain_process(h, unsafe.Pointer(&cin[0]), C.int64_t(frames),
-					unsafe.Pointer(&cout[0]), C.int64_t(bufferSize), &got)
-				if rc != C.PB_OK {
-					return 0, lastError(rc) // closes the sender and ends the run, pipe.go:438-440
+				if err := call(func() C.int32_t {
+					return C.pb_chain_process(h, pin, C.int64_t(frames), pout, C.int64_t(bufferSize), &got)
+				}); err != nil {
+					return 0, err // closes the sender and ends the run, pipe.go:438-440
 				}
-				signal.WriteFloat64(cout[:int(got)*int(outCh)], out)
+				ovals := int(got) * int(outCh)
+				if opt.Float32 {
+					for i, v := range out32[:ovals] {
+						tmp[i] = float64(v)
+					}
+					signal.WriteFloat64(tmp[:ovals], out)
+				} else {
+					signal.WriteFloat64(out64[:ovals], out)
+				}
 				return int(got), nil // a short count slices the output, pipe.go:441-443
 			},
-			FlushFunc: func(context.Context) error { // guaranteed teardown, run.go:181-185
-				C.free(unsafe.Pointer(&cin[0]))
-				C.free(unsafe.Pointer(&cout[0]))
-				if rc := C.pb_chain_destroy(h); rc != C.PB_OK {
-					return lastError(rc)
-				}
+			FlushFunc: func(context.Context) error { // run.go:181-185: everything enqueued has completed; the chain stays bound
+				defer runtime.KeepAlive(own)
 				runtime.KeepAlive(mctx)
-				return nil
+				return call(func() C.int32_t { return C.pb_chain_sync(h, nil) })
 			},
 		}, nil
 	}

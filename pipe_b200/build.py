@@ -16,7 +16,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libpipe_b200.so")
 SOURCES = ["chain.cu", "aux_kernels.cu"]
-HEADERS = ["common.cuh", "chain_tile.cuh", "chain_tc.cuh", os.path.join("..", "..", "include", "pipe_b200.h")]
+HEADERS = ["common.cuh", "chain_tile.cuh", "chain_tc.cuh", "chain_stream.cuh", os.path.join("..", "..", "include", "pipe_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math=false", "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-cudart", "static",

@@ -580,8 +580,10 @@ struct Sink : Flusher {  // mock.go:160-192
 namespace gpu {
 
 // One contiguous run of GPU Processors in Line.Processors as ONE pipe::Processor: the allocator creates the pb_chain
-// (line.go:71 -> pb_chain_create), ProcessFunc is one call across the C-ABI per buffer (pipe.go:438 -> pb_chain_process),
-// FlushFunc destroys it (run.go:181-185 -> pb_chain_destroy).  There is no CPU fallback: without a usable sm_100 device the
+// (line.go:71 -> pb_chain_create), ProcessFunc is one call across the C-ABI per buffer (pipe.go:438 -> pb_chain_process).
+// The reference binds components once and a Pipe may be started again after Wait (pipe_test.go:107-130), so the handle lives
+// as long as the Processor's closures: StartFunc of a restart zeroes the carried state (pb_chain_reset), FlushFunc
+// (run.go:181-185) only drains the device, and the last closure to go destroys the chain.  There is no CPU fallback: without a usable sm_100 device the
 // allocator fails and pipe::Run / Pipe::New return that error, as line.go:72-74 does for any allocator error.
 struct Stage {
     pb_stage_desc d{};
@@ -616,8 +618,9 @@ struct Stage {
     }
 };
 
-struct ChainHandle {  // shared by the three funcs of the Processor; destroyed by FlushFunc (or with the last reference)
+struct ChainHandle {  // shared by the three funcs of the Processor; destroyed with the last reference
     pb_chain *h = nullptr;
+    int starts = 0;
     ~ChainHandle()
     {
         if (h) pb_chain_destroy(h);
@@ -658,10 +661,12 @@ ProcessorAllocatorFunc<T> Chain(std::vector<Stage> stages, int device = 0, unsig
                 return {0, Error::New(std::string("pb_chain_process: ") + pb_last_error())};
             return {(int)got, Error::None()};
         };
-        p.FlushFunc = [ch]() -> Error {
-            pb_chain *h = ch->h;
-            ch->h = nullptr;
-            if (h && pb_chain_destroy(h) != PB_OK) return Error::New(std::string("pb_chain_destroy: ") + pb_last_error());
+        p.StartFunc = [ch]() -> Error {  // a restarted Pipe begins from zero state
+            if (ch->starts++ > 0 && pb_chain_reset(ch->h) != PB_OK) return Error::New(std::string("pb_chain_reset: ") + pb_last_error());
+            return Error::None();
+        };
+        p.FlushFunc = [ch]() -> Error {  // everything enqueued has completed; the chain stays bound for the next Start
+            if (pb_chain_sync(ch->h, nullptr) != PB_OK) return Error::New(std::string("pb_chain_sync: ") + pb_last_error());
             return Error::None();
         };
         return Error::None();

@@ -62,7 +62,7 @@ class PeerFanIn:
         if self.rank == self.dst:
             self.abi.mix_sum(self.peer_ptrs, self.dtype, self.n_values, out_ptr, device=self.device, stream=stream)
         # the caller must not overwrite its buffer before dst's kernel has read it:
-        # synchronise dst's stream, then barrier (see bench.py --fan-in)
+        # synchronise dst's stream, then barrier (see bench.py fan_in_run)
 
     def close(self):
         if self.rank == self.dst:

@@ -78,3 +78,56 @@ def test_gpu_allocator_error_aborts_binding():
     with pytest.raises(Exception) as e:
         pipe.new(16, pipe.Line(source=src.source(), processors=pipe.processors(bad), sink=snk.sink()))
     assert "processor" in str(e.value) and "UNSUPPORTED" in str(e.value)   # line.go:72-74
+
+
+def test_pipe_with_gpu_chain_restarts_from_zero_state():
+    # TestReset (pipe_test.go:107-130): Start / Wait, source.Reset(), Start again -- the chain handle stays bound across the
+    # runs (FlushFunc must not free it) and StartFunc zeroes the carried state, so both runs give the oracle's first-run output
+    ch, bs, limit = 16, 512, 3 * 512 + 77
+    stages = design.config_stages("chain4")
+
+    def fill(out, first_frame):
+        out[:] = orc.source_fill(first_frame * ch, out.size).reshape(out.shape)
+
+    src = mock.Source(limit=limit, channels=ch, sample_rate=48000.0, fill=fill)
+    snk = mock.Sink(discard=False)
+    cp = gpu.ChainProcessor(stages, dtype=np.float32)
+    p = pipe.new(bs, pipe.Line(source=src.source(), processors=pipe.processors(cp.processor()), sink=snk.sink()), dtype=np.float32)
+    x = orc.source_fill(0, limit * ch).reshape(limit, ch)
+    cpu = orc.Chain(ch, stages)
+    ref = np.concatenate([cpu.process(x[i:i + bs]) for i in range(0, limit, bs)])
+    p.start().wait()
+    first = np.array(snk.values)
+    src.reset()
+    p.start().wait()
+    both = np.array(snk.values)
+    assert cp.starts == 2 and cp.chain is not None
+    assert len(both) == 2 * len(first) == 2 * len(ref)
+    for run in (first, both[len(first):]):
+        assert (np.abs(run - ref).max(axis=0) <= 1e-6 * np.abs(ref).max(axis=0)).all()
+    cp.close()
+    assert cp.chain is None
+
+
+def test_float64_pipe_reaches_the_tcgen05_kernel_through_compute_dtype():
+    # the reference always allocates float64 buffers (pipe.go:394,437); compute_dtype=float32 converts in the marshalling copy,
+    # which is how a float64 pipe reaches K2: 128 channels x 1600-frame buffers through pipe.Line / gpu.chain, last_path == 2
+    ch, bs, limit = 128, 1600, 4 * 1600
+    stages = design.config_stages("chain4")
+
+    def fill(out, first_frame):
+        out[:] = orc.source_fill(first_frame * ch, out.size).reshape(out.shape)
+
+    src = mock.Source(limit=limit, channels=ch, sample_rate=48000.0, fill=fill)
+    snk = mock.Sink(discard=False)
+    cp = gpu.ChainProcessor(stages, dtype=np.float64, compute_dtype=np.float32)
+    pipe.run(bs, pipe.Line(source=src.source(), processors=pipe.processors(cp.processor()), sink=snk.sink()), dtype=np.float64)
+    assert cp.chain.last_path()[0] == 2
+    x = orc.source_fill(0, limit * ch).reshape(limit, ch)
+    cpu = orc.Chain(ch, stages)
+    ref = np.concatenate([cpu.process(x[i:i + bs]) for i in range(0, limit, bs)])
+    y = snk.values
+    assert y.dtype == np.float64 and len(y) == len(ref) == (limit * 147) // 160
+    for i in range(0, len(ref), len(ref) // 4):
+        seg, rseg = y[i:i + len(ref) // 4], ref[i:i + len(ref) // 4]
+        assert (np.abs(seg - rseg).max(axis=0) <= 1e-6 * np.abs(rseg).max(axis=0)).all()

@@ -21,12 +21,11 @@ for t in tiles:
         print(f"  {role:7s}", " ".join(f"{k}:{ev[k] - base}" for k in ks))
     ks = sorted(m)
     print("  mma1 d  ", " ".join(str(m[k] - m[ks[i - 1]]) if i else "-" for i, k in enumerate(ks)))
-    for role in ("mma1w", "mma1i"):   # converter leaders: 4 units x 8 points (top, raw, a1, sync, cvtA, cvtB, st, sync)
-        ev = rows.get((t, role), {})
-        for k in range(4):
-            pts = [ev.get(k * 8 + i) for i in range(8)]
-            if all(v is not None for v in pts):
-                print(f"  {role} unit {k}: start {pts[0] - base}  raw {pts[1]-pts[0]} a1 {pts[2]-pts[1]} sync {pts[3]-pts[2]} cvtA {pts[4]-pts[3]} cvtB {pts[5]-pts[4]} wait_st {pts[6]-pts[5]} sync {pts[7]-pts[6]}")
+    ev = rows.get((t, "mma1x"), {})   # MMA1 issuer internals: 4 pairs x 7 points
+    for k in range(4):
+        pts = [ev.get(k * 8 + i) for i in range(7)]
+        if all(v is not None for v in pts):
+            print(f"  mma1 pair {k}: start {pts[0] - base}  slice_wait {pts[1]-pts[0]} a1_wait {pts[2]-pts[1]} fence {pts[3]-pts[2]} elect+issueA {pts[4]-pts[3]} issueB {pts[5]-pts[4]} syncwarp {pts[6]-pts[5]}")
     w, iss = {}, {}
     if w and iss:
         print("  wait    ", " ".join(str(w[k] - m[k - 1]) if k - 1 in m and k in w else "-" for k in ks))
