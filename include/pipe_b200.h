@@ -89,7 +89,7 @@ typedef struct pb_chain_desc {
 } pb_chain_desc;
 
 #define PB_CHAIN_METER 1u       /* fused meter sink: per-channel peak and sum of squares of the output */
-#define PB_CHAIN_NO_TENSOR 2u   /* never take the tcgen05 FIR path */
+#define PB_CHAIN_NO_TENSOR 2u   /* never take the tcgen05 FIR path (exact-order float32 arithmetic instead) */
 #define PB_CHAIN_NO_STREAM 4u   /* never take the streaming kernels: the generic tile kernel serves FIR-less runs too */
 
 typedef struct pb_chain pb_chain;
@@ -116,7 +116,10 @@ int32_t pb_chain_process(pb_chain *c, const void *in_host, int64_t in_frames,
  * NULL); asynchronous with respect to the host.  n_buffers consecutive buffers
  * are processed by one launch; buffer i has buf_frames[i] frames (only the last
  * may be short, pipe.go:404-406) and its outputs follow buffer i-1's in
- * out_dev.  buf_out_frames[i] receives the per-buffer `processed` count. */
+ * out_dev.  buf_out_frames[i] receives the per-buffer `processed` count.
+ * Stream ordering: the carried state is shared with the host-buffer paths, which run on the chain's own streams.  A
+ * caller that mixes this entry point with pb_chain_process / pb_chain_submit on the same chain must call pb_chain_sync
+ * in between (one component, one caller at a time: run.go:175-194). */
 int32_t pb_chain_process_batch_device(pb_chain *c, const void *in_dev, const int64_t *buf_frames,
                                       int32_t n_buffers, void *out_dev, int64_t out_capacity_frames,
                                       int64_t *buf_out_frames, void *stream);
@@ -139,6 +142,13 @@ int32_t pb_chain_collect(pb_chain *c, int64_t *buf_out_frames, int32_t n_buffers
  * parameters of one stage; takes effect at the next process call, carried
  * state kept.  kind, n_taps and up/down must not change. */
 int32_t pb_chain_set_stage(pb_chain *c, int32_t stage_index, const pb_stage_desc *stage);
+
+/* InsertProcessor on a fused run (pipe.go:297-333; the executor side is run.go:134-169): insert `stage` at position
+ * `pos` (0 .. n_stages) of the run.  The run is re-planned into fused kernels; every stage that was already there keeps
+ * its carried state (FIR history, biquad state, resampler history and phase), the new stage starts from zero state like
+ * a freshly allocated Processor.  Takes effect at the next process call.  (AddLine, pipe.go:260-295, needs nothing here:
+ * a new Line is a new pb_chain.) */
+int32_t pb_chain_insert_stage(pb_chain *c, int32_t pos, const pb_stage_desc *stage);
 
 /* Fused meter sink (PB_CHAIN_METER): per-channel peak |y| and sum of y^2 of
  * everything emitted since create/reset, plus the frame count.  Synchronises. */
@@ -180,6 +190,8 @@ int32_t pb_memcpy_d2h(int32_t device, void *dst_host, const void *src_dev, int64
 int32_t pb_device_synchronize(int32_t device);
 /* cross-process peer access for the fan-in sum: 64-byte opaque handles */
 int32_t pb_ipc_export(int32_t device, void *ptr_dev, uint8_t handle[64]);
+/* the handle names the allocation ptr_dev lies in and pb_ipc_open returns that allocation's base: add this offset */
+int32_t pb_ipc_offset(int32_t device, void *ptr_dev, int64_t *offset);
 int32_t pb_ipc_open(int32_t device, const uint8_t handle[64], void **ptr_dev);
 int32_t pb_ipc_close(int32_t device, void *ptr_dev);
 

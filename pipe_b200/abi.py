@@ -66,6 +66,7 @@ SIGNATURES = {
     "pb_chain_submit": (_i32, [_vp, _vp, _pi64, _i32, _vp, _i64]),
     "pb_chain_collect": (_i32, [_vp, _pi64, _i32]),
     "pb_chain_set_stage": (_i32, [_vp, _i32, C.POINTER(StageDesc)]),
+    "pb_chain_insert_stage": (_i32, [_vp, _i32, C.POINTER(StageDesc)]),
     "pb_chain_meter_read": (_i32, [_vp, _pd, _pd, _pi64]),
     "pb_chain_last_path": (_i32, [_vp, _pi32, _pi64]),
     "pb_source_fill_device": (_i32, [_i32, _i32, _vp, _i64, _i64, C.c_uint64, C.c_uint64, _vp]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "pb_memcpy_d2h": (_i32, [_i32, _vp, _vp, _i64]),
     "pb_device_synchronize": (_i32, [_i32]),
     "pb_ipc_export": (_i32, [_i32, _vp, C.POINTER(C.c_uint8)]),
+    "pb_ipc_offset": (_i32, [_i32, _vp, _pi64]),
     "pb_ipc_open": (_i32, [_i32, C.POINTER(C.c_uint8), C.POINTER(_vp)]),
     "pb_ipc_close": (_i32, [_i32, _vp]),
     "pb_abi_version": (_i32, []),
@@ -182,6 +184,12 @@ class Chain:
         keep: list = []
         s = make_stage(d, keep)
         check(lib().pb_chain_set_stage(self._h, idx, C.byref(s)))
+
+    def insert_stage(self, pos: int, d: dict):
+        """InsertProcessor on the fused run (pipe.go:297): re-plans the run, existing stages keep their carried state."""
+        keep: list = []
+        s = make_stage(d, keep)
+        check(lib().pb_chain_insert_stage(self._h, pos, C.byref(s)))
 
     # -- ProcessFunc with host buffers ----------------------------------------
     def process(self, x: np.ndarray) -> np.ndarray:

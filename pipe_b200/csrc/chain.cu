@@ -1471,6 +1471,94 @@ extern "C" int32_t pb_chain_set_stage(pb_chain *c, int32_t idx, const pb_stage_d
     return PB_OK;  // a COPY stage: nothing to update
 }
 
+// Copy the carried state of the stateful stage `old_stage` of plan `olds` into whichever segment of the new plan now holds that
+// stage (`new_stage`).  State is per STAGE in meaning -- a FIR's past input, a biquad's TDF-II state, a resampler's past input
+// and phase -- and every kernel family stores it in the same form, so it survives any regrouping of the
+// stages into segments.
+static int32_t carry_stage_state(pb_chain *c, const std::vector<Segment> &olds, int old_stage, int new_stage)
+{
+    const Segment *so = nullptr;
+    Segment *sn = nullptr;
+    for (const auto &s : olds)
+        if (s.fir_stage == old_stage || s.bq_stage == old_stage || s.rs_stage == old_stage) so = &s;
+    for (auto &s : c->segs)
+        if (s.fir_stage == new_stage || s.bq_stage == new_stage || s.rs_stage == new_stage) sn = &s;
+    if (!so || !sn) return PB_OK;  // a stage without carried state (copy, gain)
+    const size_t el = c->elem;
+    if (so->fir_stage == old_stage && so->Hf > 0)
+        PB_CUDA(cudaMemcpy(sn->d_xhist[sn->pp], so->d_xhist[so->pp], el * (size_t)so->Hf * c->C, cudaMemcpyDeviceToDevice));
+    if (so->bq_stage == old_stage)
+        PB_CUDA(cudaMemcpy(sn->d_state[sn->pp], so->d_state[so->pp], sizeof(double) * (size_t)c->C * 2, cudaMemcpyDeviceToDevice));
+    if (so->rs_stage == old_stage) {
+        if (so->Hr > 0)
+            PB_CUDA(cudaMemcpy(sn->d_yhist[sn->pp], so->d_yhist[so->pp], el * (size_t)so->Hr * c->C, cudaMemcpyDeviceToDevice));
+        sn->acc = so->acc;
+    }
+    return PB_OK;
+}
+
+// InsertProcessor on a fused run (pipe.go:297-333, run.go:134-169): the run is re-planned -- the stage list is cut into fused
+// segments again, tables and workspaces are rebuilt -- and every stage that was already there keeps its carried state; the new
+// stage starts from zero state, like a freshly allocated Processor.  Takes effect at the next process call (the reference
+// applies the edit as a mutation between buffers, pipe.go:302).
+extern "C" int32_t pb_chain_insert_stage(pb_chain *c, int32_t pos, const pb_stage_desc *st)
+{
+    if (!c || !st) return fail(PB_ERR_INVALID, "pb_chain_insert_stage: NULL argument");
+    if (pos < 0 || pos > (int)c->stages.size()) return fail(PB_ERR_INVALID, "pb_chain_insert_stage: position %d of %zu", pos, c->stages.size());
+    if (c->slots_busy) return fail(PB_ERR_STATE, "pb_chain_insert_stage while submitted batches are in flight");
+    int32_t r = validate_stage(*st, pos);
+    if (r != PB_OK) return r;
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    PB_CUDA(cudaDeviceSynchronize());   // edits land between buffers: drain what is in flight first
+    StageCopy ns;
+    ns.d = *st;
+    if (st->taps && st->n_taps > 0) ns.taps.assign(st->taps, st->taps + st->n_taps);
+    ns.d.taps = nullptr;
+    std::vector<StageCopy> old_stages = c->stages;
+    std::vector<Segment> olds = std::move(c->segs);
+    void *old_mid[2] = {c->d_mid[0], c->d_mid[1]};
+    const double old_rate = c->out_sample_rate;
+    c->stages.insert(c->stages.begin() + pos, ns);
+    c->d_mid[0] = c->d_mid[1] = nullptr;
+    c->tmaps.clear();
+    plan_segments(c);
+    auto rollback = [&](int32_t code) {
+        char keep[512];
+        snprintf(keep, sizeof keep, "%s", tls_error_buf());
+        for (auto &s : c->segs) free_segment(s);
+        for (int i = 0; i < 2; i++)
+            if (c->d_mid[i]) cudaFree(c->d_mid[i]);
+        c->segs = std::move(olds);
+        c->stages = old_stages;
+        c->d_mid[0] = old_mid[0];
+        c->d_mid[1] = old_mid[1];
+        c->out_sample_rate = old_rate;
+        snprintf(tls_error_buf(), 512, "%s", keep);
+        return code;
+    };
+    double rate = c->sample_rate;
+    for (auto &s : c->segs) {
+        r = build_segment(c, s);
+        if (r != PB_OK) return rollback(r);
+        if (s.rs_stage >= 0) rate = rate * s.up / s.down;
+    }
+    if (c->segs.size() > 1)
+        for (int i = 0; i < 2; i++)
+            if (cudaMalloc(&c->d_mid[i], c->elem * (size_t)c->max_frames * c->C) != cudaSuccess)
+                return rollback(fail(PB_ERR_NOMEM, "pb_chain_insert_stage: intermediate buffers"));
+    for (int i = 0; i < (int)old_stages.size(); i++) {
+        r = carry_stage_state(c, olds, i, i < pos ? i : i + 1);
+        if (r != PB_OK) return rollback(r);
+    }
+    PB_CUDA(cudaDeviceSynchronize());
+    c->out_sample_rate = rate;
+    for (auto &s : olds) free_segment(s);
+    for (int i = 0; i < 2; i++)
+        if (old_mid[i]) cudaFree(old_mid[i]);
+    return PB_OK;
+}
+
 extern "C" int32_t pb_chain_meter_read(pb_chain *c, double *peak, double *sumsq, int64_t *frames)
 {
     if (!c) return fail(PB_ERR_INVALID, "pb_chain_meter_read: NULL chain");
@@ -1570,6 +1658,26 @@ extern "C" int32_t pb_ipc_export(int32_t device, void *ptr, uint8_t handle[64])
     cudaIpcMemHandle_t h;
     PB_CUDA(cudaIpcGetMemHandle(&h, ptr));
     memcpy(handle, &h, 64);
+    return PB_OK;
+}
+
+// cudaIpcGetMemHandle names the ALLOCATION a pointer lies in, and cudaIpcOpenMemHandle returns that allocation's base: a buffer
+// carved out of a larger block (any caching allocator) sits at this offset from it.
+extern "C" int32_t pb_ipc_offset(int32_t device, void *ptr, int64_t *offset)
+{
+    if (!ptr || !offset) return fail(PB_ERR_INVALID, "pb_ipc_offset: NULL");
+    DeviceGuard dg(device);
+    PB_CUDA(dg.err);
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    typedef CUresult (*PFN_range)(CUdeviceptr *, size_t *, CUdeviceptr);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(PB_ERR_CUDA, "cuMemGetAddressRange is unavailable");
+    const CUresult r = ((PFN_range)fn)(&base, &size, (CUdeviceptr)(uintptr_t)ptr);
+    if (r != CUDA_SUCCESS) return fail(PB_ERR_CUDA, "cuMemGetAddressRange failed (%d)", (int)r);
+    *offset = (int64_t)((uintptr_t)ptr - (uintptr_t)base);
     return PB_OK;
 }
 

@@ -43,18 +43,25 @@ class PeerFanIn:
         self.n_values, self.dtype, self.device, self.local_ptr = n_values, dtype, device, local_ptr
         handle = (abi.C.c_uint8 * 64)()
         abi.check(abi.lib().pb_ipc_export(device, local_ptr, handle))
+        # the handle names the ALLOCATION the buffer lies in (a caching allocator hands out pieces of larger blocks): the
+        # buffer's offset inside it travels with the handle
+        off = abi._i64()
+        abi.check(abi.lib().pb_ipc_offset(device, local_ptr, abi.C.byref(off)))
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=group)
+        dist.all_gather_object(handles, (bytes(handle), off.value), group=group)
         self.peer_ptrs: list[int] = []
+        self._bases: list[int] = []
         if self.rank == dst:
-            for r, h in enumerate(handles):
+            for r, (h, o) in enumerate(handles):
                 if r == dst:
                     self.peer_ptrs.append(local_ptr)
+                    self._bases.append(0)
                     continue
                 buf = (abi.C.c_uint8 * 64).from_buffer_copy(h)
                 p = abi._vp()
                 abi.check(abi.lib().pb_ipc_open(device, buf, abi.C.byref(p)))
-                self.peer_ptrs.append(p.value)
+                self._bases.append(p.value)
+                self.peer_ptrs.append(p.value + o)
 
     def sum_into(self, out_ptr: int, stream: int = 0):
         """Call on every rank after its producer kernel finished; only `dst` launches the sum."""
@@ -66,7 +73,7 @@ class PeerFanIn:
 
     def close(self):
         if self.rank == self.dst:
-            for r, p in enumerate(self.peer_ptrs):
+            for r, p in enumerate(self._bases):
                 if r != self.dst:
                     self.abi.lib().pb_ipc_close(self.device, p)
         self.peer_ptrs = []

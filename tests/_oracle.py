@@ -213,3 +213,21 @@ def pipe_run(buffer_size: int, lines: list[MockLine]) -> tuple[int, list[MockLin
 
 def mock_source_drain(buffer_size: int, line: MockLine) -> int:
     return int(lib().orc_mock_source_drain(buffer_size, C.byref(line)))
+
+
+class StageList:
+    """The oracle's chain as separate per-stage chains run one after the other (the same arithmetic: every Processor keeps its own
+    carried state), which makes pipe.InsertProcessor (pipe.go:297) trivial to restate: a new stage, with zero state, is put into
+    the list; everything that was there keeps its state."""
+
+    def __init__(self, channels: int, stages: list[dict]):
+        self.channels = channels
+        self.chains = [Chain(channels, [st]) for st in stages]
+
+    def insert(self, pos: int, stage: dict):
+        self.chains.insert(pos, Chain(self.channels, [stage]))
+
+    def process(self, x: np.ndarray, threads: int = 1) -> np.ndarray:
+        for c in self.chains:
+            x = c.process(x, threads=threads)
+        return x

@@ -698,3 +698,66 @@ def test_k2_serves_4096_frame_buffers_between_k1_head_and_tail():
         assert gpu.last_path()[0] == 2
         assert_parity(y, ref, REL_F32, f"buffer {b}")
     assert lens == [3763, 3763, 3763, 3763, 3764, 3763]
+
+
+# ------------------------------------------------ graph edits: InsertProcessor on a fused run (pipe.go:297-333) --
+
+def _edit_case(channels, bf, stages, edits, dtype=np.float32, n_buffers=6, rel=REL_F32):
+    """edits: {buffer index: (position, stage)} applied BEFORE that buffer, on the GPU chain and on the oracle's stage list."""
+    gpu = abi.Chain(channels, stages, buffer_frames=bf, dtype=dtype)
+    cpu = orc.StageList(channels, stages)
+    paths, run_peak = [], np.zeros(channels)
+    for b in range(n_buffers):
+        if b in edits:
+            pos, st = edits[b]
+            gpu.insert_stage(pos, st)
+            cpu.insert(pos, st)
+        x = signal_input(bf, channels, seed=60 + b)
+        ref = cpu.process(x)
+        run_peak = np.maximum(run_peak, np.abs(ref).max(axis=0)) if len(ref) else run_peak
+        assert gpu.peek_out_frames(bf) == len(ref)
+        y = gpu.process(x.astype(dtype))
+        assert_parity(y, ref, rel, f"buffer {b}", floor=run_peak)
+        paths.append(gpu.last_path()[0])
+    return paths
+
+
+def test_insert_processor_keeps_the_state_of_existing_stages():
+    # a gain, a second biquad and a FIR spliced into a running [gain, biquad] run: the run is re-planned (one segment, then two),
+    # the biquad that was there keeps its state across both edits, the new stages start from zero state
+    b2, a2 = design.biquad("highpass", 300.0, 48000.0, q=0.7)
+    stages = design.config_stages("gain_biquad")
+    edits = {2: (2, {"kind": "biquad", "b": b2, "a": a2}),                       # behind the existing biquad: a second segment
+             4: (0, {"kind": "fir", "taps": design.lowpass_fir(65, 0.2)})}        # in front of everything
+    paths = _edit_case(48, 1000, stages, edits)
+    assert paths[0] == 3       # the streaming kernel first; afterwards [FIR, biquad] on the generic kernel + [biquad] streaming
+
+
+def test_insert_processor_into_the_headline_chain_keeps_it_on_the_tensor_kernel():
+    # the 4-stage chain on K2; a gain in front keeps the shape (still K2, state carried through the re-plan); a second FIR in
+    # front of the first cuts the run into [gain, gain, FIR] on the generic kernel and [FIR, biquad, resample], which is still
+    # K2's shape and continues there with the state it had
+    ch, bf = 128, 1600
+    stages = design.config_stages("chain4")
+    edits = {2: (0, {"kind": "gain", "gain": 1.5}),
+             4: (2, {"kind": "fir", "taps": design.lowpass_fir(33, 0.3)})}
+    paths = _edit_case(ch, bf, stages, edits)
+    assert paths == [2] * 6
+
+
+def test_insert_processor_validation_and_float64():
+    gpu = abi.Chain(4, [{"kind": "gain", "gain": 2.0}], buffer_frames=64, dtype=np.float64)
+    with pytest.raises(abi.PipeB200Error) as e:
+        gpu.insert_stage(5, {"kind": "gain", "gain": 1.0})
+    assert e.value.code == abi.PB_ERR_INVALID
+    with pytest.raises(abi.PipeB200Error) as e:
+        gpu.insert_stage(0, {"kind": "resample", "up": 3, "down": 2, "taps": np.ones(6)})   # rejected: the run is unchanged
+    assert e.value.code == abi.PB_ERR_UNSUPPORTED
+    x = signal_input(64, 4)
+    assert np.array_equal(gpu.process(x), 2.0 * x)
+    b, a = design.biquad("lowpass", 5000.0, 48000.0)
+    paths = _edit_case(4, 256, [{"kind": "gain", "gain": 0.5}], {1: (1, {"kind": "biquad", "b": b, "a": a}),
+                                                               3: (2, {"kind": "resample", "up": 2, "down": 3,
+                                                                       "taps": design.resampler_prototype(2, 3, 8)})},
+                       dtype=np.float64, rel=REL_F64)
+    assert paths[-1] == 1
