@@ -308,14 +308,25 @@ def pcie_ceiling(nbytes: int, barrier):
 
 def dropin_e2e(local: int, n_buffers: int = 12):
     """The drop-in case, shaped like the cgo shim (go/pipeb200.go): the pipe hands over ONE pageable float64 buffer per
-    ProcessFunc call (pipe.go:394,437,438); the shim marshals it into its staging (ReadFloat64, converting to float32 in
+    ProcessFunc call (pipe.go:394,437,438); the shim marshals it into its pinned staging (ReadFloat64, converting to float32 in
     float32 mode), calls pb_chain_process (H2D, kernels, D2H, synchronous) and marshals the result back (WriteFloat64).
-    Both compute modes, timed on the host clock around the whole call sequence."""
+    Both compute modes, and for each the marshalling on one thread and cut over 8 threads by frame ranges (the shim's
+    Options.Workers: goroutines over signal.Floating.Slice views), timed on the host clock around the whole call sequence."""
+    from concurrent.futures import ThreadPoolExecutor
     from pipe_b200 import abi, design
     import _oracle as orc  # input generation only (outside the timed region)
     x64 = orc.source_fill(0, BUFFER_FRAMES * CHANNELS).reshape(BUFFER_FRAMES, CHANNELS)   # pageable float64, as signal.Floating
     out64 = np.empty_like(x64)
     res = {}
+    pool = ThreadPoolExecutor(max_workers=8)
+
+    def par_copy(dst, src, rows, workers):
+        if workers <= 1:
+            np.copyto(dst[:rows], src[:rows], casting="same_kind")
+            return
+        per = (rows + workers - 1) // workers
+        list(pool.map(lambda lo: np.copyto(dst[lo:min(rows, lo + per)], src[lo:min(rows, lo + per)], casting="same_kind"),
+                      range(0, rows, per)))   # numpy releases the GIL inside the copy
     for mode, dt in (("float64 compute (go: Chain)", np.float64), ("float32 compute (go: ChainWith{Float32: true})", np.float32)):
         chain = abi.Chain(CHANNELS, design.config_stages("chain4"), buffer_frames=BUFFER_FRAMES, dtype=dt, device=local)
         pin_in = abi.PinnedBuffer(x64.size * np.dtype(dt).itemsize)
@@ -323,24 +334,32 @@ def dropin_e2e(local: int, n_buffers: int = 12):
         a_in, a_out = pin_in.array(x64.shape, dt), pin_out.array(x64.shape, dt)
         got = abi._i64()
         lib = abi.lib()
-
-        def one():
-            np.copyto(a_in, x64, casting="same_kind")            # ReadFloat64 (+ narrowing in float32 mode)
-            abi.check(lib.pb_chain_process(chain._h, pin_in.ptr, BUFFER_FRAMES, pin_out.ptr, BUFFER_FRAMES, abi.C.byref(got)))
-            n = got.value
-            np.copyto(out64[:n], a_out[:n])                       # WriteFloat64 (+ widening)
-            return n
-        for _ in range(3):
-            one()
-        t0 = time.perf_counter()
-        for _ in range(n_buffers):
-            n = one()
-        dt_s = time.perf_counter() - t0
-        res[mode] = {"value": n_buffers * BUFFER_FRAMES * CHANNELS / dt_s / 1e6, "unit": "Msamples/s",
-                     "ms_per_buffer": 1e3 * dt_s / n_buffers, "kernel_path": chain.last_path()[0], "out_frames_last": int(n)}
+        for workers in (1, 8):
+            def one():
+                par_copy(a_in, x64, BUFFER_FRAMES, workers)              # ReadFloat64 (+ narrowing in float32 mode)
+                abi.check(lib.pb_chain_process(chain._h, pin_in.ptr, BUFFER_FRAMES, pin_out.ptr, BUFFER_FRAMES, abi.C.byref(got)))
+                n = got.value
+                par_copy(out64, a_out, n, workers)                       # WriteFloat64 (+ widening)
+                return n
+            chain.reset()
+            for _ in range(3):
+                one()
+            t0 = time.perf_counter()
+            for _ in range(n_buffers):
+                n = one()
+            dt_s = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            for _ in range(n_buffers):   # the library's share: the same calls without the marshalling copies
+                abi.check(lib.pb_chain_process(chain._h, pin_in.ptr, BUFFER_FRAMES, pin_out.ptr, BUFFER_FRAMES, abi.C.byref(got)))
+            lib_s = time.perf_counter() - t1
+            res[f"{mode}, marshalling on {workers} thread{'s' if workers > 1 else ''}"] = {
+                "value": n_buffers * BUFFER_FRAMES * CHANNELS / dt_s / 1e6, "unit": "Msamples/s",
+                "ms_per_buffer": 1e3 * dt_s / n_buffers, "ms_per_buffer_in_pb_chain_process": 1e3 * lib_s / n_buffers,
+                "kernel_path": chain.last_path()[0], "out_frames_last": int(n)}
         chain.close()
         pin_in.free()
         pin_out.free()
+    pool.shutdown()
     return res
 
 

@@ -31,6 +31,7 @@ import (
 	"context"
 	"fmt"
 	"runtime"
+	"sync"
 	"unsafe"
 
 	"pipelined.dev/pipe"
@@ -76,6 +77,33 @@ type Options struct {
 	// the float64 kernels.  See INTEGRATION.md "which kernel a chain reaches".
 	Float32 bool
 	Flags   uint32 // PB_CHAIN_*
+	// Workers is the number of goroutines the marshalling copies (ReadFloat64 / WriteFloat64, and the float32 narrowing and
+	// widening) are cut over, by frame ranges (signal.Floating.Slice gives views of the same backing buffer).  One 4096 x 1024
+	// float64 buffer is 32 MiB each way: a single goroutine moves that at memcpy speed (~3 ms per direction), several times
+	// the device's share of the call.  0 = min(GOMAXPROCS, 8).
+	Workers int
+}
+
+// parallelFrames runs f over [0, frames) cut into `workers` contiguous frame ranges, one goroutine each.
+func parallelFrames(workers, frames int, f func(lo, hi int)) {
+	if workers <= 1 || frames < 4*workers {
+		f(0, frames)
+		return
+	}
+	var wg sync.WaitGroup
+	per := (frames + workers - 1) / workers
+	for lo := 0; lo < frames; lo += per {
+		hi := lo + per
+		if hi > frames {
+			hi = frames
+		}
+		wg.Add(1)
+		go func(lo, hi int) {
+			defer wg.Done()
+			f(lo, hi)
+		}(lo, hi)
+	}
+	wg.Wait()
 }
 
 // Chain returns the ProcessorAllocatorFunc (line.go:30) for a run of GPU stages on `device`, float64 arithmetic.
@@ -159,6 +187,13 @@ func ChainWith(opt Options, stages ...Stage) pipe.ProcessorAllocatorFunc {
 			tmp = make([]float64, n)
 		}
 		starts := 0
+		workers := opt.Workers
+		if workers <= 0 {
+			workers = runtime.GOMAXPROCS(0)
+			if workers > 8 {
+				workers = 8
+			}
+		}
 
 		// The chain lives as long as the Processor: pipe binds components once (pipe.New) and a Pipe may be started again
 		// after Wait (TestReset, pipe_test.go:107-130).  The finalizer releases the device resources.
@@ -183,15 +218,20 @@ func ChainWith(opt Options, stages ...Stage) pipe.ProcessorAllocatorFunc {
 			ProcessFunc: func(in, out signal.Floating) (int, error) {
 				defer runtime.KeepAlive(own)
 				frames := in.Length()
-				vals := frames * props.Channels
-				if opt.Float32 {
-					signal.ReadFloat64(in, tmp[:vals])
-					for i, v := range tmp[:vals] {
-						in32[i] = float32(v)
+				ch := props.Channels
+				parallelFrames(workers, frames, func(lo, hi int) {
+					src := in.Slice(lo, hi)
+					if opt.Float32 {
+						t := tmp[lo*ch : hi*ch]
+						signal.ReadFloat64(src, t)
+						d := in32[lo*ch : hi*ch]
+						for i, v := range t {
+							d[i] = float32(v)
+						}
+					} else {
+						signal.ReadFloat64(src, in64[lo*ch:hi*ch])
 					}
-				} else {
-					signal.ReadFloat64(in, in64[:vals])
-				}
+				})
 				var got C.int64_t
 				// goroutines migrate between OS threads; the library selects its device on every call
 				if err := call(func() C.int32_t {
@@ -199,15 +239,19 @@ func ChainWith(opt Options, stages ...Stage) pipe.ProcessorAllocatorFunc {
 				}); err != nil {
 					return 0, err // closes the sender and ends the run, pipe.go:438-440
 				}
-				ovals := int(got) * int(outCh)
-				if opt.Float32 {
-					for i, v := range out32[:ovals] {
-						tmp[i] = float64(v)
+				och := int(outCh)
+				parallelFrames(workers, int(got), func(lo, hi int) {
+					dst := out.Slice(lo, hi) // a view of out's backing buffer (out arrives at full length, pipe.go:437)
+					if opt.Float32 {
+						t := tmp[lo*och : hi*och]
+						for i, v := range out32[lo*och : hi*och] {
+							t[i] = float64(v)
+						}
+						signal.WriteFloat64(t, dst)
+					} else {
+						signal.WriteFloat64(out64[lo*och:hi*och], dst)
 					}
-					signal.WriteFloat64(tmp[:ovals], out)
-				} else {
-					signal.WriteFloat64(out64[:ovals], out)
-				}
+				})
 				return int(got), nil // a short count slices the output, pipe.go:441-443
 			},
 			FlushFunc: func(context.Context) error { // run.go:181-185: everything enqueued has completed; the chain stays bound

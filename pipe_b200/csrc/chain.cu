@@ -66,6 +66,7 @@ struct Segment {
     bool st_ok = false;
     int st_grid = 0;
     void *d_st_tab = nullptr;                        // StTab
+    void *d_scan_blk = nullptr;                      // K3 two sweeps: block aggregates of the scan [groups][kScanBlocks][32][2] doubles
     double st_wt[32][2] = {};                        // A^k B, passed in the kernel parameters
 };
 
@@ -188,7 +189,7 @@ static void plan_segments(pb_chain *c)
 static void free_segment(Segment &s)
 {
     void *ptrs[] = {s.d_taps, s.d_wt, s.d_apow, s.d_coef, s.d_xhist[0], s.d_xhist[1], s.d_yhist[0], s.d_yhist[1],
-                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables, s.d_tc_rc, s.d_st_tab,
+                    s.d_state[0], s.d_state[1], s.d_agg, s.d_inc, (void *)s.d_status, s.d_tc_tables, s.d_tc_rc, s.d_st_tab, s.d_scan_blk,
                     (void *)s.d_tc_scale, (void *)s.d_tc_peak};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -216,14 +217,18 @@ static int32_t configure_kernel(pb_chain *c, Segment &s)
 template <typename T>
 static cudaError_t configure_stream_kernels(int *per_sm)
 {
-    cudaError_t e = cudaSuccess;
-    if (kStDynSmem > 0) {
-        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(chain_stream_kernel<T, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStDynSmem)) != cudaSuccess) return e;
-    }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, chain_stream_kernel<T, 0>, kStThreads, kStDynSmem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, chain_stream_kernel<T, 0, kStOneSweep>, kStThreads, 0);
+}
+
+// one launch of chain_stream_kernel in the given mode; the channel counts of BASELINE.json's configs get row addresses with
+// immediate offsets
+template <typename T, int MODE>
+static void launch_stream_mode(const StreamParams<T> &p, int grid, int C, cudaStream_t stream)
+{
+    if (C == 1024) chain_stream_kernel<T, 1024, MODE><<<grid, kStThreads, 0, stream>>>(p);
+    else if (C == 256) chain_stream_kernel<T, 256, MODE><<<grid, kStThreads, 0, stream>>>(p);
+    else if (C == 64) chain_stream_kernel<T, 64, MODE><<<grid, kStThreads, 0, stream>>>(p);
+    else chain_stream_kernel<T, 0, MODE><<<grid, kStThreads, 0, stream>>>(p);
 }
 
 // ---- K2 host side --------------------------------------------------------------
@@ -669,15 +674,16 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
             std::vector<long long> tr((size_t)tc::kTraceTiles * tc::kTraceRoles * 32);
             PB_CUDA(cudaMemcpy(tr.data(), p.trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
             long long t0 = 0;
+            const long long kRawTag = 1ll << 62;   // entries above this are raw values, not clocks
             for (long long v : tr)
-                if (v && (!t0 || v < t0)) t0 = v;
+                if (v && v < kRawTag && (!t0 || v < t0)) t0 = v;
             static const char *roles[] = {"mma1", "cvt0", "cvt1", "drainA", "drainB", "mma2", "out"};
             for (int ti = 0; ti < tc::kTraceTiles; ti++)
                 for (int r = 0; r < tc::kTraceRoles; r++) {
                     fprintf(stderr, "[PB_TC_TRACE] tile %d %-6s", ti, roles[r]);
                     for (int k = 0; k < 32; k++) {
                         const long long v = tr[((size_t)ti * tc::kTraceRoles + r) * 32 + k];
-                        if (v) fprintf(stderr, " %d:%lld", k, v - t0);
+                        if (v) fprintf(stderr, " %d:%lld", k, v >= kRawTag ? v - kRawTag : v - t0);
                     }
                     fprintf(stderr, "\n");
                 }
@@ -829,6 +835,7 @@ static int32_t build_segment(pb_chain *c, Segment &s)
         PB_CUDA(cudaMalloc(&s.d_wt, sizeof(double) * (size_t)s.wt_len * 2));
         s.lb_tiles = (int)ceil_div64(c->max_frames, std::min(s.L, s.st_ok ? kStMinTile : kTcFrames)) + 1;
         if (s.st_ok) PB_CUDA(cudaMalloc(&s.d_st_tab, sizeof(double) * (size_t)StTab::kCount));
+        if (s.st_ok) PB_CUDA(cudaMalloc(&s.d_scan_blk, sizeof(double) * 64 * (size_t)kScanBlocks * ((size_t)(c->C + kCg - 1) / kCg)));
         const size_t groups = (size_t)(c->C + kCg - 1) / kCg;
         PB_CUDA(cudaMalloc(&s.d_agg, sizeof(double) * groups * s.lb_tiles * 64));
         PB_CUDA(cudaMalloc(&s.d_inc, sizeof(double) * groups * s.lb_tiles * 64));
@@ -989,12 +996,31 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
     p.err_flag = reinterpret_cast<int *>(c->d_ticket + 1);
     if (has_bq && p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int64_t total = (int64_t)p.n_tiles * p.n_groups;
-    const int grid = (int)std::min<int64_t>(total, s.st_grid);
-    // the channel counts of BASELINE.json's configs get row addresses with immediate offsets
-    if (c->C == 1024) chain_stream_kernel<T, 1024><<<grid, kStThreads, kStDynSmem, stream>>>(p);
-    else if (c->C == 256) chain_stream_kernel<T, 256><<<grid, kStThreads, kStDynSmem, stream>>>(p);
-    else if (c->C == 64) chain_stream_kernel<T, 64><<<grid, kStThreads, kStDynSmem, stream>>>(p);
-    else chain_stream_kernel<T, 0><<<grid, kStThreads, kStDynSmem, stream>>>(p);
+    // PB_ST_CTAS_PER_SM=<n>: fewer resident CTAs (fewer tiles in flight, a shorter look-back), for measurements
+    static const int ctas_per_sm = getenv("PB_ST_CTAS_PER_SM") ? atoi(getenv("PB_ST_CTAS_PER_SM")) : 0;
+    const int grid = (int)std::min<int64_t>(total, ctas_per_sm > 0 ? std::min(s.st_grid, ctas_per_sm * c->num_sms) : s.st_grid);
+    // With few channel groups hundreds of tiles of one group are in flight and the look-back of a single sweep is what the launch
+    // waits for: two sweeps with a scan in between instead (chain_stream.cuh, kStOneSweep).  PB_ST_TWO_SWEEPS=<groups> moves the
+    // threshold (0: never), for measurements.
+    static const int two_sweep_groups = getenv("PB_ST_TWO_SWEEPS") ? atoi(getenv("PB_ST_TWO_SWEEPS")) : 4;
+    if (has_bq && p.n_groups <= two_sweep_groups && p.n_tiles >= 256) {
+        launch_stream_mode<T, kStAggregate>(p, grid, c->C, stream);
+        PB_CUDA(cudaGetLastError());
+        c->ticket_base += (unsigned long long)total + (unsigned long long)grid * kStTicketsPerCta;
+        p.ticket_base = c->ticket_base;
+        // block aggregates: the first kScanBlocks slots of the (otherwise unused) inclusive-state array of the LAST tile row would
+        // alias live data, so they have their own scratch behind the look-back arrays
+        const dim3 sgrid((unsigned)p.n_groups, (unsigned)kScanBlocks);
+        stream_scan_kernel<0><<<sgrid, kScanWarps * 32, 0, stream>>>(p.lb_agg, p.lb_inc, (double *)s.d_scan_blk, p.bq_state, p.tab, c->C,
+                                                                     p.n_tiles, p.n_tiles - 1);
+        stream_scan_kernel<1><<<sgrid, kScanWarps * 32, 0, stream>>>(p.lb_agg, p.lb_inc, (double *)s.d_scan_blk, p.bq_state, p.tab, c->C,
+                                                                     p.n_tiles, p.n_tiles - 1);
+        PB_CUDA(cudaGetLastError());
+        launch_stream_mode<T, kStApply>(p, grid, c->C, stream);
+        c->launches += 3;
+    } else {
+        launch_stream_mode<T, kStOneSweep>(p, grid, c->C, stream);
+    }
     PB_CUDA(cudaGetLastError());
     c->ticket_base += (unsigned long long)total + (unsigned long long)grid * kStTicketsPerCta;
     c->launches++;

@@ -11,8 +11,8 @@
 //                         f64: 32 KB in, 32 KB out); the R rows of each of the 8 warps go from HBM straight into the warp's
 //                         slab of shared memory (cp.async, 16 B per lane, no register staging: 48 registers, 5 CTAs per SM),
 //                         are read from there by both passes and leave as one coalesced 128 B / 256 B store per row, so
-//                         one HBM read and one HBM write per sample is all the traffic there is (PB_ST_SMEM = 0 keeps the
-//                         rows in registers instead: 3 CTAs per SM, measured slower).  The biquad (TDF-II, double, the same carried
+//                         one HBM read and one HBM write per sample is all the traffic there is (keeping the rows in
+//                         registers instead, 3 CTAs per SM, measured slower).  The biquad (TDF-II, double, the same carried
 //                         state [C][2] as K1/K2) is parallelised in time as in K1: zero-state end state of every R-row
 //                         sub-chunk (2 independent DFMA per sample), tile aggregate, decoupled look-back across tiles, the
 //                         true recursion from the resolved state (5 DFMA per sample).  What differs from K1, because the
@@ -36,28 +36,27 @@
 
 namespace pb {
 
+// Tuning history (profiles/r01_k3_summary.md; the measured-slower variants live outside the shipped kernel now): the tile waits
+// between its two passes in shared memory (cp.async, 5 CTAs per SM: 65 % of the HBM peak at 1024 ch; in registers 57 %; two tiles
+// with the next one's copies in flight 40 %, because a CTA that holds a ticket it is not yet working on publishes that tile's
+// aggregate a whole tile late); every warp walks one look-back window (a two-level walk over blocks of 32 tiles read 1/32 of the
+// payloads and still measured slower: the payload loads are not what a tile waits for).
 #ifndef PB_ST_ROWS32
-#define PB_ST_ROWS32 32   // rows per warp for f32 (tuning switches, see profiles/)
-#endif
-// Where a tile waits between its two passes (measured on gain + biquad, 1024 ch f32, profiles/r01_k3_summary.md):
-//   1  in shared memory, copied there by cp.async, 5 CTAs per SM                                  65 % of the HBM peak
-//   0  in registers (32 rows per thread), 3 CTAs per SM                                           57 %
-//   2  two tiles in shared memory, the next tile's copies and ticket in flight, 3 CTAs per SM     40 %: a CTA that holds
-//      a ticket it is not yet working on publishes that tile's aggregate a whole tile late, and its successors wait
-#ifndef PB_ST_SMEM
-#define PB_ST_SMEM 1
-#endif
-// Look-back: 0 = every warp walks one window of 32 predecessors (default); 1 = two levels (blocks of 32 tiles, see st_poll).
-// The two-level walk reads 1/32 of the payloads and needs one batch of payload loads per warp, yet it measured SLOWER
-// (1024 ch: 57.3 % vs 64.7 %, configs[1]: 27.6 % vs 31.5 %; with the own-block walk on one warp 53.6 %): the payload loads
-// are not what a tile waits for (profiles/r01_k3_summary.md).  Kept as a measured alternative.
-#ifndef PB_ST_BLOCKS
-#define PB_ST_BLOCKS 0
+#define PB_ST_ROWS32 32   // rows per warp for f32
 #endif
 #ifndef PB_ST_MINB
-#define PB_ST_MINB (PB_ST_SMEM == 2 ? 3 : PB_ST_SMEM ? 5 : 3)  // resident CTAs per SM the register budget is set for
+#define PB_ST_MINB 5      // resident CTAs per SM the register budget is set for
 #endif
-constexpr int kStTicketsPerCta = PB_ST_SMEM == 2 ? 2 : 1;  // tickets a CTA draws past the end of the batch
+// How the tiles of a launch learn their incoming biquad state:
+//   kStOneSweep   decoupled look-back inside one launch (8 B of HBM traffic per f32 sample).  Right when there are many channel
+//                 groups: the tiles in flight spread over them and the walk is short (1024 ch: 65 % of the HBM peak).
+//   kStAggregate + stream_scan_kernel + kStApply ("two sweeps")   with FEW channel groups (configs[1]: 64 ch = 2 groups) hundreds
+//                 of tiles of one group are in flight, every tile folds up to 256 predecessors and the launch sits at 33 % of the
+//                 peak waiting for them.  Reading the input twice costs 12 B per sample but nothing ever waits: sweep 1 stores
+//                 every tile's aggregate, a one-CTA-per-group scan turns them into inclusive states, sweep 2 (in REVERSE tile
+//                 order: the end of the batch is what sweep 1 left in L2) runs the recursion from the resolved states.
+enum : int { kStOneSweep = 0, kStAggregate = 1, kStApply = 2 };
+constexpr int kStTicketsPerCta = 1;  // tickets a CTA draws past the end of the batch
 constexpr int kStThreads = 256;
 constexpr int kStWarps = kStThreads / 32;        // 8 sub-chunks per tile, and 8 look-back windows
 constexpr int kStWin = 32;                       // look-back window (one predecessor per lane)
@@ -67,7 +66,6 @@ struct StShape {
     static constexpr int kTile = kStWarps * kRows;            // frames per tile: 256 (f32) / 128 (f64)
 };
 constexpr int kStMinTile = 128;
-constexpr int kStDynSmem = PB_ST_SMEM == 2 ? 2 * 32 * 1024 : 0;  // both dtypes: 8 warps x R rows x 32 channels = 32 KB per tile
 
 // double tables in global memory, copied to shared memory at kernel start (dynamic indices)
 struct StTab {
@@ -192,71 +190,6 @@ __device__ __noinline__ double2 st_slide(const unsigned *st_g, const double *agg
     }
 }
 
-// ---- two-level look-back (PB_ST_BLOCKS) ------------------------------------------------------------------------------------
-// Tiles are grouped in blocks of 32.  The last tile of a block (the "closer") publishes, in its aggregate slot, the fold of the
-// WHOLE block instead of its own aggregate.  A tile then resolves its incoming state from (a) the aggregates of the tiles in
-// front of it inside its own block (at most 31, stride 1) and (b) one entry per earlier block (stride 32): the block fold, or
-// the closer's inclusive state, which ends the walk.  With two channel groups several hundred tiles of a group are in flight:
-// walking them one by one cost 1.9 GB of L2 reads per 0.34 GB of input (configs[1]); the block hops need 1/32 of that.
-
-// Lane i watches tile base - i * stride, for i < limit.  Returns the position of the first inclusive state, or `limit` when
-// all `limit` positions hold aggregates; -1 on timeout.  Positions before the stream start (tile index < 0) count as
-// inclusive: their payload is the state the call started from.  ignore_inc: the closer folds its block's aggregates only.
-__device__ __forceinline__ int st_poll(const unsigned *st_g, int base, int stride, int limit, bool ignore_inc, int lane, unsigned epoch,
-                                       int *err_flag)
-{
-    const int j = base - lane * stride;
-    for (unsigned spins = 0;; spins++) {
-        unsigned st = kLbAgg;  // lanes past the limit: ready, never inclusive
-        if (lane < limit) {
-            st = kLbInc;
-            if (j >= 0) {
-                st = ld_acquire_u32(st_g + j);
-                st = ((st >> 2) == epoch) ? (st & 3u) : kLbNone;
-                if (ignore_inc && st == kLbInc) st = kLbAgg;
-            }
-        }
-        const unsigned ready = __ballot_sync(0xffffffffu, st != kLbNone);
-        const unsigned inc = __ballot_sync(0xffffffffu, st == kLbInc);
-        if (inc) {
-            const int first_inc = __ffs(inc) - 1;
-            const unsigned need = (first_inc == 0) ? 0u : (0xffffffffu >> (32 - first_inc));
-            if ((ready & need) == need) return first_inc;
-        } else if (ready == 0xffffffffu) {
-            return limit;
-        }
-        if (spins > (1u << 24)) {  // ~1 s: a predecessor never published
-            if (lane == 0) atomicExch(err_flag, 1);
-            return -1;
-        }
-        __nanosleep(32);
-    }
-}
-
-// w += sum_{i < count} mt[i] Z_{base - i stride}  (+ mt[count] Inc_{base - count stride} when terminal), this lane's channel
-__device__ __forceinline__ void st_fold(const double *agg_g, const double *inc_g, const double *init, const double *mt, int base, int stride,
-                                        int count, bool terminal, int lane, double &w0, double &w1)
-{
-#pragma unroll 1
-    for (int i0 = 0; i0 < count; i0 += 4) {  // payloads four at a time: one L2 round trip per batch is exposed
-        double2 a[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = (i0 + u < count) ? i0 + u : count - 1;
-            a[u] = __ldcg(reinterpret_cast<const double2 *>(agg_g + (size_t)(base - i * stride) * 64 + lane * 2));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (i0 + u < count) mat2_fma(mt + 4 * (i0 + u), a[u].x, a[u].y, w0, w1);
-    }
-    if (terminal) {
-        const int jt = base - count * stride;
-        const double2 q = jt < 0 ? (init ? *reinterpret_cast<const double2 *>(init) : make_double2(0.0, 0.0))
-                                 : __ldcg(reinterpret_cast<const double2 *>(inc_g + (size_t)jt * 64 + lane * 2));
-        mat2_fma(mt + 4 * count, q.x, q.y, w0, w1);
-    }
-}
-
 // This warp's rows of `tile` go straight from HBM into its slab of shared memory (cp.async, no register staging): 16 B per
 // lane, four (f64: two) rows per instruction; rows past the end and channels past C are zero-filled (src-size 0).
 template <typename T>
@@ -302,26 +235,18 @@ __device__ __forceinline__ void st_issue_tile(const StreamParams<T> &p, int C, i
 }
 
 // CC: the channel count when it is one of the instantiated constants (then every row address is base + immediate: the
-// 64-bit address arithmetic per row was a quarter of all instructions), 0 for any other count.
-template <typename T, int CC>
+// 64-bit address arithmetic per row was a quarter of all instructions), 0 for any other count.  MODE: see kStOneSweep.
+template <typename T, int CC, int MODE>
 __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(const __grid_constant__ StreamParams<T> p)
 {
     constexpr int R = StShape<T>::kRows, kTile = StShape<T>::kTile;
     __shared__ double tab_s[StTab::kCount];
     __shared__ double zq_s[kStWarps * kCg * 2];    // zero-state end state of every sub-chunk; reused for the meter partials
-    __shared__ double part_s[(kStWarps + 1) * kCg * 2];  // look-back partial of every window / slice (+ the hops)
+    __shared__ double part_s[kStWarps * kCg * 2];  // look-back partial of every window
     __shared__ double zsum_s[kCg * 2];             // tile aggregate, parked by warp 0 across the look-back
     __shared__ int flag_s[kStWarps];               // window w held an inclusive state (the combination stops there)
-#if PB_ST_SMEM == 2
-    __shared__ int s_next[2];
-    extern __shared__ __align__(16) unsigned char xs_raw[];  // 2 x 32 KB: two tiles, one slab of R rows per warp in each
-    T *xs = reinterpret_cast<T *>(xs_raw);
-#elif PB_ST_SMEM
     __shared__ int s_tile;
     __shared__ __align__(16) T xs[kStWarps * R * kCg];  // 32 KB: the tile, one slab of R rows per warp
-#else
-    __shared__ int s_tile;
-#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = CC ? CC : p.C;
@@ -331,43 +256,18 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
         for (int i = tid; i < StTab::kCount; i += kStThreads) tab_s[i] = p.tab[i];
     const double *pw_s = tab_s + StTab::kPw, *lb_s = tab_s + StTab::kLb, *mw_s = tab_s + StTab::kMw;
 
-#if PB_ST_SMEM == 2
-    // Software pipeline over this CTA's tiles: the copies of the NEXT tile are in flight while the current one is processed,
-    // and the ticket after that is already being fetched.  s_next[k & 1] holds the ticket of the CTA's k-th tile.
-    if (tid == 0) {
-        s_next[0] = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-        s_next[1] = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-    }
-    __syncthreads();
-    if (s_next[0] < total_tiles) st_issue_tile<T>(p, C, s_next[0], xs + warp * R * kCg, warp, lane);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int k = 0;; k++) {
-        const int tile = s_next[k & 1];
-        if (tile >= total_tiles) break;
-        __syncthreads();  // every thread has read s_next[k & 1]; the previous tile is done with the small shared arrays
-        const int nxt = s_next[(k + 1) & 1];
-        if (tid == 0) s_next[k & 1] = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);  // the CTA's tile k + 2
-        // a warp's slab is read by that warp only, so the buffer of tile k - 1 is free in program order
-        if (nxt < total_tiles) st_issue_tile<T>(p, C, nxt, xs + (((k + 1) & 1) * kStWarps + warp) * R * kCg, warp, lane);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's copies have landed
-        __syncwarp();  // a row is read by other lanes than the ones that copied it
-        T *xs_w = xs + ((k & 1) * kStWarps + warp) * R * kCg;
-#else
     for (;;) {
         __syncthreads();  // previous tile done with shared memory (and the tables visible)
         if (tid == 0) s_tile = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
         __syncthreads();
-        const int tile = s_tile;
-        if (tile >= total_tiles) break;
-#if PB_ST_SMEM
+        if (s_tile >= total_tiles) break;
+        // One sweep: time-major tickets -- a tile only waits on smaller tickets, which resident CTAs already hold.  Second of two
+        // sweeps: nothing waits, and the batch is walked backwards (see kStApply).
+        const int tile = MODE == kStApply ? total_tiles - 1 - s_tile : s_tile;
         T *xs_w = xs + warp * R * kCg;
         st_issue_tile<T>(p, C, tile, xs_w, warp, lane);
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();  // a row is read by other lanes than the ones that copied it
-#endif
-#endif
-        // time-major tickets: a tile only waits on smaller tickets, which resident CTAs already hold
         const int t = tile / p.n_groups, g = tile - t * p.n_groups;
         const bool first = (t == 0), last = (t == p.n_tiles - 1);
         const int64_t f0 = (int64_t)t * kTile;
@@ -380,215 +280,118 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
         const int64_t ld = C;  // a compile-time constant when CC != 0
 
         T *dst = p.out + (f0 + r0) * ld + c;
-#if PB_ST_SMEM
         const T gl = p.g_load;  // the leading gains are applied when a row is read
 #define PB_XV(i) (xs_w[(i) * kCg + lane] * gl)
 #define PB_XR(i) xs_w[(i) * kCg + lane]  // biquad runs: the host folds the leading gains into wt and b0..b2 (one FMUL per read less)
-#else
-        // ---- this warp's rows: R independent coalesced loads, scaled by the leading gains; rows past the end are zero
-        T x[R];
-        const T *src = p.in + (f0 + r0) * ld + c;
-        if (full) {
-#pragma unroll
-            for (int i = 0; i < R; i++) x[i] = __ldcs(src + i * ld);
-        } else {
-#pragma unroll
-            for (int i = 0; i < R; i++) x[i] = (cvalid && i < nrow) ? __ldcs(src + i * ld) : T(0);
-        }
-        if (p.g_load != T(1)) {
-#pragma unroll
-            for (int i = 0; i < R; i++) x[i] *= p.g_load;
-        }
-#define PB_XV(i) x[i]
-#define PB_XR(i) x[i]
-#endif
         double m_peak = 0.0, m_sumsq = 0.0;
 
         if (p.has_bq) {
             // ---- pass 1: zero-state end state of the sub-chunk (the zero rows past the end of a ragged chunk leave its sum
             //      unused: only full tiles are chained, and the stream's final state comes out of pass 2)
             {
-                double z0 = 0.0, z1 = 0.0, y0 = 0.0, y1 = 0.0;  // two accumulator pairs: shorter dependent chains
+                // four accumulator pairs: a dependent DFMA costs ~100 cycles here, the chains must be short
+                double z0 = 0.0, z1 = 0.0, y0 = 0.0, y1 = 0.0, u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
 #pragma unroll
-                for (int i = 0; i < R; i += 2) {
-                    const double xa = (double)PB_XR(i), xb = (double)PB_XR(i + 1);
+                for (int i = 0; i < R; i += 4) {
+                    const double xa = (double)PB_XR(i), xb = (double)PB_XR(i + 1), xc = (double)PB_XR(i + 2), xd = (double)PB_XR(i + 3);
                     z0 = fma(p.wt[R - 1 - i][0], xa, z0);
                     z1 = fma(p.wt[R - 1 - i][1], xa, z1);
                     y0 = fma(p.wt[R - 2 - i][0], xb, y0);
                     y1 = fma(p.wt[R - 2 - i][1], xb, y1);
+                    u0 = fma(p.wt[R - 3 - i][0], xc, u0);
+                    u1 = fma(p.wt[R - 3 - i][1], xc, u1);
+                    v0 = fma(p.wt[R - 4 - i][0], xd, v0);
+                    v1 = fma(p.wt[R - 4 - i][1], xd, v1);
                 }
-                *reinterpret_cast<double2 *>(zq_s + (warp * kCg + lane) * 2) = make_double2(z0 + y0, z1 + y1);
+                *reinterpret_cast<double2 *>(zq_s + (warp * kCg + lane) * 2) = make_double2((z0 + y0) + (u0 + v0), (z1 + y1) + (u1 + v1));
             }
             __syncthreads();
-            // ---- warp 0: the tile aggregate sum_q A^(R (7-q)) z_q, published at once (it depends on nothing) and parked in
-            //      shared memory until the inclusive state is due
             const size_t slot = (size_t)g * p.n_tiles + t;
-            if (warp == 0) {
+            if (MODE != kStApply && warp == 0) {
+                // ---- warp 0: the tile aggregate sum_q A^(R (7-q)) z_q, published at once (it depends on nothing) and parked in
+                //      shared memory until the inclusive state is due
                 double Z0 = 0.0, Z1 = 0.0;
 #pragma unroll
                 for (int q = 0; q < kStWarps; q++) {
                     const double2 z = *reinterpret_cast<const double2 *>(zq_s + (q * kCg + lane) * 2);
                     mat2_fma(pw_s + 4 * (kStWarps - 1 - q), z.x, z.y, Z0, Z1);
                 }
-                *reinterpret_cast<double2 *>(zsum_s + lane * 2) = make_double2(Z0, Z1);
-#if PB_ST_BLOCKS
-                // the closer of a block publishes the fold of the whole block, once it has it (below); the stream's first
-                // tile leaves its payload for the closer of block 0 and goes straight to an inclusive state
-                if (!last && (t & 31) != 31) {
+                if (MODE == kStAggregate) {
+                    // first of two sweeps: the aggregate is all this launch wants from the tile (the scan reads full tiles only)
                     *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
-                    __syncwarp();
-                    if (lane == 0 && !first) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
-                }
-#else
-                if (!last && !first) {
-                    // payload by every lane, then ONE release by lane 0: the warp barrier orders the lanes' stores before it
-                    *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
-                    __syncwarp();
-                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
-                }
-#endif
-            }
-#if PB_ST_BLOCKS
-            // ---- look-back, two levels (see st_poll): the (at most 31) tiles in front of this one inside its block are cut
-            //      into slices of 4, one per warp -- one poll and one batch of payloads each, no exchange between the warps:
-            //      the combination below simply stops at the first slice that ended at an inclusive state; the last warp then
-            //      hops over the closers of the earlier blocks
-            const int m_own = t & 31;
-            const bool closer = (m_own == 31);
-            {
-                const unsigned *st_g = p.lb_status + (size_t)g * p.n_tiles;
-                const double *agg_g = p.lb_agg + (size_t)g * p.n_tiles * 64, *inc_g = p.lb_inc + (size_t)g * p.n_tiles * 64;
-                const double *init = cvalid ? p.bq_state + 2 * c : nullptr;
-                double w0 = 0.0, w1 = 0.0;
-                int terminal = 0;
-                if (first) {
-                    if (warp == 0) {
-                        terminal = 1;
-                        if (cvalid) {
-                            w0 = p.bq_state[2 * c];
-                            w1 = p.bq_state[2 * c + 1];
-                        }
-                    }
                 } else {
-                    const int left = m_own - 4 * warp, cnt = left < 0 ? 0 : (left > 4 ? 4 : left);
-                    if (cnt > 0) {
-                        int fi = st_poll(st_g, t - 1 - 4 * warp, 1, cnt, closer, lane, p.epoch, p.err_flag);
-                        __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
-                        if (fi < 0) fi = 0;
-                        terminal = fi < cnt;
-                        st_fold(agg_g, inc_g, init, lb_s, t - 1 - 4 * warp, 1, fi, terminal, lane, w0, w1);
-                    }
-                }
-                *reinterpret_cast<double2 *>(part_s + (warp * kCg + lane) * 2) = make_double2(w0, w1);
-                if (lane == 0) flag_s[warp] = terminal;
-                if (closer && !last) {
-                    // the closer publishes the fold of the whole block, Z_t + A^T (fold of the 31 tiles in front), BEFORE
-                    // the hops: the closers of later blocks must not wait for this tile's own look-back
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (warp == 0) {
-                        double W0 = 0.0, W1 = 0.0;
-#pragma unroll
-                        for (int q = 0; q < kStWarps; q++) {
-                            const double2 v = *reinterpret_cast<const double2 *>(part_s + (q * kCg + lane) * 2);
-                            mat2_fma(lb_s + 16 * q, v.x, v.y, W0, W1);
-                        }
-                        const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
-                        double B0 = Z.x, B1 = Z.y;
-                        mat2_fma(lb_s + 4, W0, W1, B0, B1);
-                        *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(B0, B1);
+                    *reinterpret_cast<double2 *>(zsum_s + lane * 2) = make_double2(Z0, Z1);
+                    if (!last && !first) {
+                        // payload by every lane, then ONE release by lane 0: the warp barrier orders the lanes' stores before it
+                        *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
                         __syncwarp();
                         if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
                     }
                 }
-                if (warp == kStWarps - 1) {
-                    // closers of the earlier blocks: tiles base, base - 32, ...; 32 hops per round (1024 tiles)
-                    double h0 = 0.0, h1 = 0.0;
-                    if (!first) {
-                        double M[4] = {1.0, 0.0, 0.0, 1.0};
-                        for (int base = t - m_own - 1;; base -= 32 * kStWin) {
-                            const int fi = st_poll(st_g, base, 32, kStWin, false, lane, p.epoch, p.err_flag);
-                            __syncwarp();
-                            if (fi < 0) break;
-                            double v0 = 0.0, v1 = 0.0;
-                            st_fold(agg_g, inc_g, init, mw_s, base, 32, fi, fi < kStWin, lane, v0, v1);
-                            mat2_fma(M, v0, v1, h0, h1);
-                            if (fi < kStWin) break;
-                            const double *ML = mw_s + 4 * kStWin;  // M <- M (A^T)^1024
-                            const double n0 = M[0] * ML[0] + M[1] * ML[2], n1 = M[0] * ML[1] + M[1] * ML[3];
-                            const double n2 = M[2] * ML[0] + M[3] * ML[2], n3 = M[2] * ML[1] + M[3] * ML[3];
-                            M[0] = n0; M[1] = n1; M[2] = n2; M[3] = n3;
-                        }
-                    }
-                    *reinterpret_cast<double2 *>(part_s + (kStWarps * kCg + lane) * 2) = make_double2(h0, h1);
-                }
             }
-            __syncthreads();
-            // ---- incoming state of the tile: the slices in order up to the first one that ended at an inclusive state;
-            //      if none did, (A^T)^m_own times what the hops found
-            double S0 = 0.0, S1 = 0.0;
-            {
-                bool term = false;
-#pragma unroll 1
-                for (int q = 0; q < kStWarps && !term; q++) {
-                    const double2 v = *reinterpret_cast<const double2 *>(part_s + (q * kCg + lane) * 2);
-                    mat2_fma(lb_s + 16 * q, v.x, v.y, S0, S1);
-                    term = flag_s[q] != 0;
-                }
-                if (!term) {
-                    const double2 h = *reinterpret_cast<const double2 *>(part_s + (kStWarps * kCg + lane) * 2);
-                    mat2_fma(lb_s + 4 * m_own, h.x, h.y, S0, S1);
-                }
-            }
-#else
-            // ---- look-back: warp w resolves window w of this group's predecessors (rotating the windows so that warp 0,
-            //      which has just paid for the aggregate and its release, takes the farthest one measured no gain)
-            {
-                const int win = warp;  // tiles t-1-32 win .. t-32-32 win
-                double w0 = 0.0, w1 = 0.0;
-                int terminal = 1;
+            if (MODE == kStAggregate) continue;
+            double S0 = 0.0, S1 = 0.0;  // incoming state of the tile
+            if (MODE == kStApply) {
+                // the scan left the inclusive state after every full tile in lb_inc
                 if (first) {
-                    if (win == 0 && cvalid) {
-                        w0 = p.bq_state[2 * c];
-                        w1 = p.bq_state[2 * c + 1];
+                    if (cvalid) {
+                        S0 = p.bq_state[2 * c];
+                        S1 = p.bq_state[2 * c + 1];
                     }
                 } else {
-                    const unsigned *st_g = p.lb_status + (size_t)g * p.n_tiles;
-                    const double *agg_g = p.lb_agg + (size_t)g * p.n_tiles * 64, *inc_g = p.lb_inc + (size_t)g * p.n_tiles * 64;
-                    const int base = t - 1 - kStWin * win;
-                    if (base >= 0) {
-                        const int first_inc = st_poll_window(st_g, base, lane, p.epoch, p.err_flag);
-                        __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
-                        if (first_inc >= 0) st_fold_window(agg_g, inc_g, lb_s, base, first_inc, lane, w0, w1);
-                        terminal = first_inc < kStWin;
-                        if (win == kStWarps - 1 && !terminal) {
-                            const double2 r = st_slide(st_g, agg_g, inc_g, lb_s, base, lane, p.epoch, p.err_flag, w0, w1);
-                            w0 = r.x;
-                            w1 = r.y;
-                            terminal = 1;
+                    const double2 q = __ldcg(reinterpret_cast<const double2 *>(p.lb_inc + (slot - 1) * 64 + lane * 2));
+                    S0 = q.x;
+                    S1 = q.y;
+                }
+            } else {
+                // ---- look-back: warp w resolves window w of this group's predecessors (rotating the windows so that warp 0,
+                //      which has just paid for the aggregate and its release, takes the farthest one measured no gain)
+                {
+                    const int win = warp;  // tiles t-1-32 win .. t-32-32 win
+                    double w0 = 0.0, w1 = 0.0;
+                    int terminal = 1;
+                    if (first) {
+                        if (win == 0 && cvalid) {
+                            w0 = p.bq_state[2 * c];
+                            w1 = p.bq_state[2 * c + 1];
+                        }
+                    } else {
+                        const unsigned *st_g = p.lb_status + (size_t)g * p.n_tiles;
+                        const double *agg_g = p.lb_agg + (size_t)g * p.n_tiles * 64, *inc_g = p.lb_inc + (size_t)g * p.n_tiles * 64;
+                        const int base = t - 1 - kStWin * win;
+                        if (base >= 0) {
+                            const int first_inc = st_poll_window(st_g, base, lane, p.epoch, p.err_flag);
+                            __syncwarp();  // the acquires of all lanes are ordered before every lane's payload loads
+                            if (first_inc >= 0) st_fold_window(agg_g, inc_g, lb_s, base, first_inc, lane, w0, w1);
+                            terminal = first_inc < kStWin;
+                            if (win == kStWarps - 1 && !terminal) {
+                                const double2 r = st_slide(st_g, agg_g, inc_g, lb_s, base, lane, p.epoch, p.err_flag, w0, w1);
+                                w0 = r.x;
+                                w1 = r.y;
+                                terminal = 1;
+                            }
                         }
                     }
+                    *reinterpret_cast<double2 *>(part_s + (win * kCg + lane) * 2) = make_double2(w0, w1);
+                    if (lane == 0) flag_s[win] = terminal;
                 }
-                *reinterpret_cast<double2 *>(part_s + (win * kCg + lane) * 2) = make_double2(w0, w1);
-                if (lane == 0) flag_s[win] = terminal;
-            }
-            __syncthreads();
-            // ---- incoming state of the tile: the windows' partials up to the first one that held an inclusive state
-            double S0 = 0.0, S1 = 0.0;
+                __syncthreads();
+                // ---- incoming state of the tile: the windows' partials up to the first one that held an inclusive state
 #pragma unroll 1
-            for (int w = 0; w < kStWarps; w++) {
-                const double2 v = *reinterpret_cast<const double2 *>(part_s + (w * kCg + lane) * 2);
-                mat2_fma(mw_s + 4 * w, v.x, v.y, S0, S1);
-                if (flag_s[w]) break;
-            }
-#endif
-            if (warp == 0 && !last) {
-                // inclusive state after this (full) tile
-                const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
-                double I0 = Z.x, I1 = Z.y;
-                mat2_fma(pw_s + 4 * kStWarps, S0, S1, I0, I1);
-                *reinterpret_cast<double2 *>(p.lb_inc + slot * 64 + lane * 2) = make_double2(I0, I1);
-                __syncwarp();
-                if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
+                for (int w = 0; w < kStWarps; w++) {
+                    const double2 v = *reinterpret_cast<const double2 *>(part_s + (w * kCg + lane) * 2);
+                    mat2_fma(mw_s + 4 * w, v.x, v.y, S0, S1);
+                    if (flag_s[w]) break;
+                }
+                if (warp == 0 && !last) {
+                    // inclusive state after this (full) tile
+                    const double2 Z = *reinterpret_cast<const double2 *>(zsum_s + lane * 2);
+                    double I0 = Z.x, I1 = Z.y;
+                    mat2_fma(pw_s + 4 * kStWarps, S0, S1, I0, I1);
+                    *reinterpret_cast<double2 *>(p.lb_inc + slot * 64 + lane * 2) = make_double2(I0, I1);
+                    __syncwarp();
+                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
+                }
             }
             // ---- pass 2: the recursion itself from the true state at the first row of the sub-chunk,
             //      A^(R w) S + sum_{q<w} A^(R (w-1-q)) z_q
@@ -643,6 +446,8 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                     }
                 }
         }
+#undef PB_XV
+#undef PB_XR
         if (meter) {
             __syncthreads();  // zq_s is reused: slower warps may still be reading the sub-chunk sums for their prefix
             zq_s[(warp * kCg + lane) * 2] = m_peak;
@@ -661,6 +466,120 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
             }
         }
     }
+}
+
+// Between the two sweeps: inclusive state after every full tile, S_t = (A^T) S_{t-1} + Z_t.  A dependent DFMA costs ~100 cycles
+// on this part, so the recursion is cut three ways until no chain is long: the tiles of a channel group into kScanBlocks blocks
+// (one CTA each), a block into 32 segments (one warp each, lane = channel).  PHASE 0: segment aggregates by Horner, prefix over
+// the block's segments from a zero state, block aggregate to global memory.  PHASE 1: the block's start state from the carried
+// state and the aggregates of the blocks in front, the same prefix from it, then every warp walks its segment again and stores
+// the inclusive states.  Payloads (L2, ~700 cycles) are fetched a batch ahead of the recursion.
+constexpr int kScanWarps = 32, kScanBatch = 4, kScanBlocks = 16;
+template <bool STORE>
+__device__ __forceinline__ void scan_walk(const double *agg_g, double *inc_g, int t0, int t1, double m0, double m1, double m2, double m3,
+                                          double &s0, double &s1)
+{
+    double2 A[kScanBatch], B[kScanBatch];
+    auto load = [&](double2 (&v)[kScanBatch], int tb) {
+#pragma unroll
+        for (int u = 0; u < kScanBatch; u++) {
+            const int t = tb + u < t1 ? tb + u : t1 - 1;
+            v[u] = __ldcg(reinterpret_cast<const double2 *>(agg_g + (size_t)t * 64));
+        }
+    };
+    auto run = [&](const double2 (&v)[kScanBatch], int tb) {
+#pragma unroll
+        for (int u = 0; u < kScanBatch; u++)
+            if (tb + u < t1) {
+                const double n0 = fma(m0, s0, fma(m1, s1, v[u].x)), n1 = fma(m2, s0, fma(m3, s1, v[u].y));
+                s0 = n0;
+                s1 = n1;
+                if (STORE) *reinterpret_cast<double2 *>(inc_g + (size_t)(tb + u) * 64) = make_double2(s0, s1);
+            }
+    };
+    if (t0 >= t1) return;
+    load(A, t0);
+    for (int tb = t0; tb < t1; tb += 2 * kScanBatch) {
+        if (tb + kScanBatch < t1) load(B, tb + kScanBatch);
+        run(A, tb);
+        if (tb + 2 * kScanBatch < t1) load(A, tb + 2 * kScanBatch);
+        run(B, tb + kScanBatch);
+    }
+}
+__device__ __forceinline__ void mat2_pow(const double (&M)[4], int e, double (&P)[4])
+{
+    double B[4] = {M[0], M[1], M[2], M[3]};
+    P[0] = 1.0; P[1] = 0.0; P[2] = 0.0; P[3] = 1.0;
+    for (; e > 0; e >>= 1) {
+        if (e & 1) {
+            const double r0 = P[0] * B[0] + P[1] * B[2], r1 = P[0] * B[1] + P[1] * B[3], r2 = P[2] * B[0] + P[3] * B[2],
+                         r3 = P[2] * B[1] + P[3] * B[3];
+            P[0] = r0; P[1] = r1; P[2] = r2; P[3] = r3;
+        }
+        const double q0 = B[0] * B[0] + B[1] * B[2], q1 = B[0] * B[1] + B[1] * B[3], q2 = B[2] * B[0] + B[3] * B[2],
+                     q3 = B[2] * B[1] + B[3] * B[3];
+        B[0] = q0; B[1] = q1; B[2] = q2; B[3] = q3;
+    }
+}
+// blk: [n_groups][kScanBlocks][32 lanes][2] block aggregates (scratch in global memory)
+template <int PHASE>
+__global__ void __launch_bounds__(kScanWarps * 32) stream_scan_kernel(const double *__restrict__ agg, double *__restrict__ inc,
+                                                                      double *__restrict__ blk, const double *__restrict__ bq_state,
+                                                                      const double *__restrict__ tab, int C, int n_tiles, int n_full)
+{
+    __shared__ double seg_s[kScanWarps][kCg][2];
+    __shared__ double start_s[kScanWarps][kCg][2];
+    const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = g * kCg + lane;
+    const double *AT = tab + StTab::kPw + 4 * kStWarps;   // the tile step A^T
+    const double M[4] = {AT[0], AT[1], AT[2], AT[3]};
+    const int span = (n_full + kScanBlocks - 1) / kScanBlocks;   // tiles per block
+    const int b0 = b * span < n_full ? b * span : n_full, b1 = b0 + span < n_full ? b0 + span : n_full;
+    const int per = (span + kScanWarps - 1) / kScanWarps;        // tiles per segment
+    const int t0 = b0 + w * per < b1 ? b0 + w * per : b1, t1 = t0 + per < b1 ? t0 + per : b1;
+    const double *agg_g = agg + (size_t)g * n_tiles * 64 + lane * 2;
+    double *inc_g = inc + (size_t)g * n_tiles * 64 + lane * 2;
+    double *blk_g = blk + ((size_t)g * kScanBlocks) * 64 + lane * 2;
+    double a0 = 0.0, a1 = 0.0;
+    scan_walk<false>(agg_g, inc_g, t0, t1, M[0], M[1], M[2], M[3], a0, a1);
+    seg_s[w][lane][0] = a0;
+    seg_s[w][lane][1] = a1;
+    __syncthreads();
+    if (w == 0) {
+        double P[4];
+        mat2_pow(M, per, P);
+        double s0 = 0.0, s1 = 0.0;
+        if (PHASE == 1) {
+            // start state of the block: the carried state through the blocks in front (every block in front of this one is full)
+            double Q[4];
+            mat2_pow(M, span, Q);
+            s0 = c < C ? bq_state[2 * c] : 0.0;
+            s1 = c < C ? bq_state[2 * c + 1] : 0.0;
+            for (int k = 0; k < b; k++) {
+                const double2 z = __ldcg(reinterpret_cast<const double2 *>(blk_g + (size_t)k * 64));
+                const double n0 = fma(Q[0], s0, fma(Q[1], s1, z.x)), n1 = fma(Q[2], s0, fma(Q[3], s1, z.y));
+                s0 = n0;
+                s1 = n1;
+            }
+        }
+        for (int k = 0; k < kScanWarps; k++) {
+            start_s[k][lane][0] = s0;
+            start_s[k][lane][1] = s1;
+            // the step over segment k: A^T to the number of tiles it holds (`per`, fewer in the block's last segment, none behind it)
+            const int left = b1 - (b0 + k * per), nk = left < 0 ? 0 : (left > per ? per : left);
+            if (nk == 0) continue;
+            double R[4] = {P[0], P[1], P[2], P[3]};
+            if (nk != per) mat2_pow(M, nk, R);
+            const double n0 = fma(R[0], s0, fma(R[1], s1, seg_s[k][lane][0])), n1 = fma(R[2], s0, fma(R[3], s1, seg_s[k][lane][1]));
+            s0 = n0;
+            s1 = n1;
+        }
+        if (PHASE == 0) *reinterpret_cast<double2 *>(blk_g + (size_t)b * 64) = make_double2(s0, s1);   // used when the block is full
+    }
+    if (PHASE == 0) return;
+    __syncthreads();
+    double s0 = start_s[w][lane][0], s1 = start_s[w][lane][1];
+    scan_walk<true>(agg_g, inc_g, t0, t1, M[0], M[1], M[2], M[3], s0, s1);
 }
 
 // out = g * in over a flat buffer of n values (g == 1: a copy, bit-exact).  V is the 16-byte vector of T.

@@ -682,6 +682,47 @@ def test_k3_full_batch_at_baseline_size(channels, nb):
     d_out.free()
 
 
+@pytest.mark.parametrize("dtype,channels", [(np.float32, 64), (np.float64, 64), (np.float32, 40), (np.float32, 100)])
+def test_k3_two_sweeps_with_few_channel_groups(dtype, channels):
+    # At most 4 channel groups (<= 128 ch) and >= 256 tiles per launch: the run takes two sweeps with a scan in between instead
+    # of the look-back (chain_stream.cuh, kStOneSweep).  Ragged last buffer (its tile is not chained), three launches in a row
+    # (the carried state crosses launches), the fused meter, a channel count that is not a multiple of 32, both dtypes.
+    bf = 4096
+    sizes = [bf] * 33 + [1234]      # f32: 528 full tiles + a ragged one; f64: 1056 + 1
+    b, a = design.biquad("highpass", 20.0, 48000.0, q=0.707)
+    stages = [{"kind": "gain", "gain": 0.8}, {"kind": "biquad", "b": b, "a": a}, {"kind": "gain", "gain": 1.25}]
+    gpu = abi.Chain(channels, stages, buffer_frames=bf, max_batch=len(sizes), dtype=dtype, flags=abi.CHAIN_METER)
+    cpu = orc.Chain(channels, stages)
+    total = sum(sizes)
+    el = np.dtype(dtype).itemsize
+    d_in, d_out = abi.DeviceBuffer(total * channels * el), abi.DeviceBuffer(total * channels * el)
+    refs = []
+    for rep in range(3):
+        x = signal_input(total, channels, seed=20 + rep)
+        ref = cpu.process(x, threads=os.cpu_count() or 1)
+        refs.append(ref)
+        d_in.upload(x.astype(dtype))
+        counts = gpu.process_batch_device(d_in.ptr, sizes, d_out.ptr, total)
+        gpu.sync()
+        assert counts == sizes and gpu.last_path() == (3, 4 + 4 * rep)   # sweep, scan (two launches), sweep
+        y = d_out.download((total, channels), dtype)
+        pos = 0
+        for i, n in enumerate(sizes):
+            # float64: the 20 Hz high-pass has poles 0.002 from the unit circle; in the TDF-II basis the powers A^k that carry a
+            # state across 128 rows have entries of order 1e2 and the states they produce are 1e-3 of the signal, so the
+            # time-parallel form loses ~5 digits to cancellation that the sequential oracle does not: 7e-11 measured in two sweeps,
+            # 9e-11 in one (tools/k3_f64_cond.py; 1e-13 for a 200 Hz high-pass, 5e-16 for an 8 kHz low-pass).  Well-conditioned filters hold 1e-12 (test_k3_gain_biquad_stream_path).
+            assert_parity(y[pos:pos + n], ref[pos:pos + n], REL_F32 if dtype == np.float32 else 2e-10, f"launch {rep} buffer {i}")
+            pos += n
+    peak, sumsq, frames = gpu.meter_read()
+    rp, rs = orc.meter(np.concatenate(refs))
+    assert frames == 3 * total
+    np.testing.assert_allclose(peak, rp, rtol=2e-6)
+    np.testing.assert_allclose(sumsq, rs, rtol=2e-6)
+    d_in.free()
+    d_out.free()
+
+
 def test_k2_serves_4096_frame_buffers_between_k1_head_and_tail():
     # bufferSize 4096 is not a multiple of K2's 160-frame tile and the resampler phase returns to 0 only every fifth buffer:
     # every call is cut into a K1 head (to the next multiple of 160 in the stream), a K2 middle and a K1 tail.  Bit-exact frame
