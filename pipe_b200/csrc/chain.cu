@@ -10,6 +10,7 @@
 #include <memory>
 #include <mutex>
 #include <new>
+#include <map>
 #include <vector>
 
 #include "chain_stream.cuh"
@@ -62,6 +63,16 @@ struct Segment {
     unsigned *d_tc_peak = nullptr;                   // [2][C]
     int tc_k = 0;                                    // copy the next call's pass A reads
     std::vector<float> tc_rc;                        // [147 + 32][8] output correction per block state (see chain_tc.cuh)
+    // K2 tiles start at the first frame of a call, whatever the resampler's integer phase is there (160 input frames give 147
+    // outputs from ANY phase): the resampler-dependent tables (P blocks, rc, the grid shift of P) exist once per phase a chain
+    // has met, built on first use -- 4096-frame buffers visit 5 of the 160 phases
+    struct TcPhase {
+        void *d_tables = nullptr;                    // Toeplitz pieces (a copy) + P blocks of this phase, TcTables::kBytes
+        void *d_rc = nullptr;
+        int sh2 = 0;
+        bool ok = false;                             // the slice schedule covers every output at this phase
+    };
+    std::map<int, TcPhase> tc_phase;
     // K3 (streaming kernels): runs without FIR and without resampler
     bool st_ok = false;
     int st_grid = 0;
@@ -193,6 +204,11 @@ static void free_segment(Segment &s)
                     (void *)s.d_tc_scale, (void *)s.d_tc_peak};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (auto &kv : s.tc_phase) {
+        if (kv.second.d_tables) cudaFree(kv.second.d_tables);
+        if (kv.second.d_rc) cudaFree(kv.second.d_rc);
+    }
+    s.tc_phase.clear();
 }
 
 template <typename T, int FB>
@@ -257,7 +273,9 @@ static void split_fixed3(double v, __half &p0, __half &p1, __half &p2)
     p2 = __float2half_rn((float)(r1 - (double)__half2float(p1)));
 }
 
-static int32_t build_tc_tables(pb_chain *c, Segment &s)
+// ph == nullptr: everything that does not depend on the resampler phase (Toeplitz pieces of the FIR, the biquad's block-state
+// matrices, the level check); ph != nullptr: the tables of the tiles that start at integer phase acc0 of the resampler.
+static int32_t build_tc_tables(pb_chain *c, Segment &s, int acc0 = 0, Segment::TcPhase *ph = nullptr)
 {
     const auto &fir = c->stages[s.fir_stage];
     std::vector<double> h(kTcMaxTaps, 0.0);
@@ -287,12 +305,12 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
                 split_fixed3(gtap(8 * e + n_i - k_i + 1) * sh, T0[idx], T1[idx], T2[idx]);
                 T3[idx] = __float2half_rn((float)(gtap(8 * e + n_i - k_i + 1) * sh));
             }
-    PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    if (!ph) PB_CUDA(cudaMemcpy(s.d_tc_tables, tab.data(), tab.size() * sizeof(__half), cudaMemcpyHostToDevice));
     // K2's fixed-point grids make its error relative to the level INSIDE the chain (FIR output at full scale), because the
     // biquad is folded into the resampler matrix P.  A biquad that removes most of a broadband signal (a 120 Hz low-pass on
     // white noise: -29 dB) would leave that error standing against a much smaller output, so such chains stay on K1:
     // the L2 norm of the biquad's impulse response (its gain for white input) must be at least -6 dB.
-    {
+    if (!ph) {
         double s1 = 0, s2 = 0, e2 = 0;
         for (int n = 0; n < 1 << 14; n++) {
             const double x = n == 0 ? 1.0 : 0.0, y = s.b[0] * x + s1;
@@ -312,12 +330,15 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     const auto &rs = c->stages[s.rs_stage];
     auto rtap = [&](int row, int m) -> double {
         if (m >= kTcOut || row < 0 || row >= kTcN) return 0.0;
-        const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1;
+        // the integer accumulator starts the tile at acc0: after tile frame i it has seen acc0 + 147 (i + 1), output m leaves at
+        // the first i where that reaches 160 (m + 1), with what is left over as the accumulator (pipe_oracle.c, resampler)
+        const int im = (kTcFrames * (m + 1) - acc0 + kTcUp - 1) / kTcUp - 1;
         const int k = im + kTcHr - row;
         if (k < 0 || k >= kTcP) return 0.0;
-        const int br = kTcUp - 1 - (((im + 1) * kTcUp) % kTcFrames);
+        const int br = kTcUp - 1 - (acc0 + (im + 1) * kTcUp - kTcFrames * (m + 1));
         return rs.taps[(size_t)br + (size_t)k * kTcUp];
     };
+    auto trigger = [&](int m) { return (kTcFrames * (m + 1) - acc0 + kTcUp - 1) / kTcUp - 1; };
     double g[16], Apow[kTcN + 1][4];
     {
         double Mk[4] = {1, 0, 0, 1};
@@ -352,9 +373,11 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
             }
         int sh2 = 0;
         if (mx > 0) sh2 = (int)std::floor(std::log2(std::min(2047.0 / mx, 8191.0 / smax)));
-        s.tc_sh2 = std::max(-24, std::min(24, sh2));
+        sh2 = std::max(-24, std::min(24, sh2));
+        if (ph) ph->sh2 = sh2;
+        else s.tc_sh2 = sh2;
     }
-    const double sh2 = std::ldexp(1.0, s.tc_sh2);
+    const double sh2 = std::ldexp(1.0, ph ? ph->sh2 : s.tc_sh2);
     std::vector<__half> b2((size_t)TcTables::kB2);
     auto fill_pair = [&](int pair, int sl, int chunk, bool first0) {
         for (int n = 0; n < kRsN; n++)
@@ -375,12 +398,18 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
     fill_pair(kRsPairs, 0, 0, true);
     // every tap of every output must be inside the blocks its slice reads
     for (int m = 0; m < kTcOut; m++) {
-        const int im = ((m + 1) * kTcFrames + kTcUp - 1) / kTcUp - 1, sl = m / kRsN;
+        const int im = trigger(m), sl = m / kRsN;
         const int lo = im, hi = im + kTcHr, nch = (sl == kRsSlices - 1) ? 3 : 4;
-        if (lo < 32 * sl || hi >= 32 * sl + 16 * nch) return fail(PB_ERR_UNSUPPORTED, "resampler slice schedule does not cover output %d", m);
+        if (im < 0 || im >= kTcFrames || lo < 32 * sl || hi >= 32 * sl + 16 * nch)
+            return fail(PB_ERR_UNSUPPORTED, "resampler slice schedule does not cover output %d at phase %d", m, acc0);
     }
-    PB_CUDA(cudaMemcpy((char *)s.d_tc_tables + (size_t)TcTables::kHalfs * 2, b2.data(), b2.size() * sizeof(__half),
-                       cudaMemcpyHostToDevice));
+    if (ph) {
+        PB_CUDA(cudaMalloc(&ph->d_tables, (size_t)TcTables::kBytes));
+        PB_CUDA(cudaMalloc(&ph->d_rc, (size_t)kTcRcRows * 8 * sizeof(float)));
+        PB_CUDA(cudaMemcpy(ph->d_tables, s.d_tc_tables, (size_t)TcTables::kHalfs * 2, cudaMemcpyDeviceToDevice));
+        PB_CUDA(cudaMemcpy((char *)ph->d_tables + (size_t)TcTables::kHalfs * 2, b2.data(), b2.size() * sizeof(__half),
+                           cudaMemcpyHostToDevice));
+    }
     // Block states.  The free response of a block to the state s at its start is y_sr[i] = (A^i s)[0], i = 0..15: a 16 x 2
     // matrix H.  With H = U S V^T the states travel as w = W s, W = S V^T ("balanced" coordinates): y_sr = U w with
     // orthonormal U, so neither the tables below nor the float arithmetic on w see the cancellation that the TDF-II basis
@@ -419,10 +448,11 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
             Wi[q] = V[0][q] / S[q];          // s = V S^-1 w
             Wi[2 + q] = V[1][q] / S[q];
         }
-        for (int i = 0; i < 4; i++) {
-            s.tc_Wb[i] = W[i];
-            s.tc_Wbi[i] = Wi[i];
-        }
+        if (!ph)
+            for (int i = 0; i < 4; i++) {
+                s.tc_Wb[i] = W[i];
+                s.tc_Wbi[i] = Wi[i];
+            }
         const double gg = s.g[2] * s.g[3];
         s.tc_rc.assign((size_t)kTcRcRows * 8, 0.f);
         for (int m = 0; m < kTcOut; m++)
@@ -446,7 +476,11 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s)
             s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 0] = (float)(rtap(kTcHr, m) * U[0][0] * gg);  // block 0: only row 15, y_sr = U[0] w
             s.tc_rc[(size_t)(kTcRcFirst + m) * 8 + 1] = (float)(rtap(kTcHr, m) * U[0][1] * gg);
         }
-        PB_CUDA(cudaMemcpy(s.d_tc_rc, s.tc_rc.data(), s.tc_rc.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (ph) {
+            PB_CUDA(cudaMemcpy(ph->d_rc, s.tc_rc.data(), s.tc_rc.size() * sizeof(float), cudaMemcpyHostToDevice));
+            ph->ok = true;
+            return PB_OK;
+        }
         auto sim = [&](const double *M, double *out) {  // W M W^-1
             double t[4] = {W[0] * M[0] + W[1] * M[2], W[0] * M[1] + W[1] * M[3], W[2] * M[0] + W[3] * M[2], W[2] * M[1] + W[3] * M[3]};
             out[0] = t[0] * Wi[0] + t[1] * Wi[2];
@@ -550,6 +584,8 @@ static int32_t tc_configure_once(int device)
             err[device] = cudaFuncSetAttribute(chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
         if (err[device] == cudaSuccess)
             err[device] = cudaFuncSetAttribute(chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+        if (err[device] == cudaSuccess)
+            err[device] = cudaFuncSetAttribute(chain_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     });
     PB_CUDA(err[device]);
     return PB_OK;
@@ -571,10 +607,30 @@ static int32_t tc_reset_scales(pb_chain *c, Segment &s, cudaStream_t stream)
     return PB_OK;
 }
 
-// One K2 call: `n` (a multiple of 160) input frames of segment `s`, as two launches of the same kernel: pass A with the scales the
+// The tables of the tiles that start at resampler phase acc0 (built on first use; *out == nullptr with PB_OK when the slice schedule
+// does not cover that phase -- the caller then falls back to tiles that start at phase 0).
+static int32_t tc_get_phase(pb_chain *c, Segment &s, int acc0, const Segment::TcPhase **out)
+{
+    auto it = s.tc_phase.find(acc0);
+    if (it == s.tc_phase.end()) {
+        Segment::TcPhase ph;
+        const int32_t r = build_tc_tables(c, s, acc0, &ph);
+        if (r != PB_OK && r != PB_ERR_UNSUPPORTED) return r;
+        if (r != PB_OK) {
+            if (ph.d_tables) cudaFree(ph.d_tables);
+            if (ph.d_rc) cudaFree(ph.d_rc);
+            ph = Segment::TcPhase();
+        }
+        it = s.tc_phase.emplace(acc0, ph).first;
+    }
+    *out = it->second.ok ? &it->second : nullptr;
+    return PB_OK;
+}
+
+// One K2 call: `n` (>= 160) input frames of segment `s`, starting at the resampler phase s.acc, as two launches of the same kernel: pass A with the scales the
 // previous call ended with, pass B which verifies them and returns at once unless a channel left its grid window (chain_tc.cuh).
-static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_t n, void *out, bool is_last_segment,
-                                 cudaStream_t stream)
+static int32_t launch_segment_tc(pb_chain *c, Segment &s, const Segment::TcPhase &ph, const void *in, int64_t n, void *out,
+                                 bool is_last_segment, cudaStream_t stream)
 {
     int32_t r = tc_configure_once(c->device);
     if (r != PB_OK) return r;
@@ -584,7 +640,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     r = cached_frame_map(c, &p.tm_hist, s.d_xhist[s.pp], s.Hf);
     if (r != PB_OK) return r;
     p.out = (float *)out;
-    p.tables = (const __half *)s.d_tc_tables;
+    p.tables = (const __half *)ph.d_tables;
     p.yhist = (const float *)s.d_yhist[s.pp];
     p.yhist_next = (float *)s.d_yhist[s.pp ^ 1];
     p.xhist_next = (float *)s.d_xhist[s.pp ^ 1];
@@ -602,13 +658,17 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
     p.peak_next = s.d_tc_peak + (size_t)(s.tc_k ^ 1) * c->C;
     p.err_flag = reinterpret_cast<int *>(c->d_ticket + 1);
     p.C = c->C;
-    p.n_tiles = (int)(n / kTcFrames);
+    // the last tile may be partial: TMA zero-fills the rows behind the call's last frame, the kernel stores only the outputs the
+    // real frames trigger and takes the carried state at the last real row
+    p.n_tiles = (int)((n + kTcFrames - 1) / kTcFrames);
+    p.last_frames = (int)(n - (int64_t)(p.n_tiles - 1) * kTcFrames);
+    p.last_outputs = (int)((s.acc + (int64_t)p.last_frames * kTcUp) / kTcFrames);
     p.n_cg = c->C / kTcCh;
     p.hist_rows = s.Hf;
     p.g_load = (float)s.g[0];
     p.fscale = (float)(s.g[1] / std::ldexp(1.0, s.tc_sh));
     p.inv_gbq = (float)(1.0 / s.g[2]);
-    p.descale_rs = (float)(s.g[2] * s.g[3] / std::ldexp(1.0, s.tc_sh2));
+    p.descale_rs = (float)(s.g[2] * s.g[3] / std::ldexp(1.0, ph.sh2));
     p.b0 = s.b[0]; p.b1 = s.b[1]; p.b2 = s.b[2]; p.a1 = s.a[0]; p.a2 = s.a[1];
     p.g_bq = s.g[2];
     for (int i = 0; i < 4; i++) {
@@ -625,7 +685,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         p.Wb[i] = s.tc_Wb[i];
         p.Wbi[i] = s.tc_Wbi[i];
     }
-    p.rc = (const float *)s.d_tc_rc;
+    p.rc = (const float *)ph.d_rc;
     if (p.n_tiles > s.lb_tiles) return fail(PB_ERR_CAPACITY, "batch of %lld frames exceeds the chain's max_batch", (long long)n);
     const int total = p.n_tiles * p.n_cg;
     const int grid = std::min(total, c->num_sms);
@@ -652,6 +712,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const void *in, int64_
         p.meter_sumsq = mtr ? mtr + c->C : nullptr;
         if (prof_mode == 1) chain_tc_kernel<1><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
         else if (prof_mode == 2) chain_tc_kernel<2><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+        else if (p.last_frames < kTcFrames) chain_tc_kernel<0, true><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
         else chain_tc_kernel<0><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
         PB_CUDA(cudaGetLastError());
         c->launches++;
@@ -772,7 +833,15 @@ static int32_t refresh_segment_params(pb_chain *c, Segment &s)
             for (int k = 0; k < s.P; k++) coef[(size_t)br * s.P + k] = st.taps[(size_t)br + (size_t)k * s.up];
         PB_CUDA(upload_any(c->dtype, s.d_coef, coef));
     }
-    if (s.tc_ok) return build_tc_tables(c, s);
+    if (s.tc_ok) {
+        // the per-phase tables hold the biquad, the resampler taps and the gains behind them: rebuilt on next use
+        for (auto &kv : s.tc_phase) {
+            if (kv.second.d_tables) cudaFree(kv.second.d_tables);
+            if (kv.second.d_rc) cudaFree(kv.second.d_rc);
+        }
+        s.tc_phase.clear();
+        return build_tc_tables(c, s);
+    }
     return PB_OK;
 }
 
@@ -1091,11 +1160,26 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
             // (the f pieces of MMA2 are fp16: the FIR output of a channel at its grid peak, |g_fir| sum|h| * 2047, must stay inside)
             const bool tc_eligible = s.tc_ok && s.g[2] != 0.0 && s.g[0] != 0.0 && s.tc_level_ok && std::fabs(s.g[1]) * s.tc_fir_l1 <= 28.0 &&
                                      ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
+            // The tiles start at the first frame of the call, with the tables of the resampler phase found there (160 frames give
+            // 147 outputs from any phase); what is left behind the last whole tile (< 160 frames) goes through K1.  Only if the
+            // slice schedule did not cover a phase would the call be cut at the next phase-0 position instead (K1 head).
             int64_t head = 0;
-            if (tc_eligible)
-                while (head < s.down && (s.acc + head * s.up) % s.down != 0) head++;
-            const int64_t mid = (tc_eligible && n - head >= kTcFrames) ? ((n - head) / kTcFrames) * kTcFrames : 0;
+            const Segment::TcPhase *ph = nullptr;
             int32_t r = PB_OK;
+            if (tc_eligible && n >= kTcFrames) {
+                r = tc_get_phase(c, s, (int)s.acc, &ph);
+                if (r != PB_OK) return r;
+                if (!ph) {
+                    while (head < s.down && (s.acc + head * s.up) % s.down != 0) head++;
+                    if (n - head >= kTcFrames) {
+                        r = tc_get_phase(c, s, 0, &ph);
+                        if (r != PB_OK) return r;
+                    }
+                }
+            }
+            // PB_TC_TAIL_K1=1 (development): whole tiles only, the rest of the call on K1 as before
+            static const bool tail_k1 = getenv("PB_TC_TAIL_K1") && atoi(getenv("PB_TC_TAIL_K1")) != 0;
+            const int64_t mid = !ph ? 0 : tail_k1 ? ((n - head) / kTcFrames) * kTcFrames : n - head;
             if (mid > 0) {
                 const int64_t acc0 = s.acc, pieces[3] = {head, mid, n - head - mid};
                 const char *from = (const char *)src;
@@ -1103,7 +1187,7 @@ static int32_t run_batch_device(pb_chain *c, const void *in_dev, const int64_t *
                 for (int k = 0; k < 3 && r == PB_OK; k++) {
                     const int64_t len = pieces[k];
                     if (len == 0) continue;
-                    r = (k == 1) ? launch_segment_tc(c, s, from, len, to, lastseg, stream) : generic(from, len, to);
+                    r = (k == 1) ? launch_segment_tc(c, s, *ph, from, len, to, lastseg, stream) : generic(from, len, to);
                     const int64_t tot = s.acc + len * s.up;  // the phase each piece starts from, restored below
                     from += (size_t)len * c->C * c->elem;
                     to += (size_t)(tot / s.down) * c->C * c->elem;

@@ -78,6 +78,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
 #include <utility>
 
 #include "chain_tile.cuh"
@@ -140,6 +141,8 @@ struct TcParams {
     int dbg;             // development switches (PB_TC_DBG): bit0 skip MMA1, bit1 skip MMA2, bit2 skip the conversion, bit4 skip the TMA loads
     int C, n_tiles, n_cg;
     int hist_rows;       // rows of xhist == FIR taps - 1 (<= 256)
+    int last_frames;     // input frames the call's last tile really holds (1..160; the rows behind them are zero-filled by TMA)
+    int last_outputs;    // outputs those frames trigger at the call's resampler phase (<= 147): the rest of that tile is not stored
     unsigned epoch;
     float g_load;        // gain applied to the frames of this call (history frames are already gain-scaled)
     float fscale;        // (E + X) -> FIR output on the channel's grid: g_fir / 2^sh
@@ -410,9 +413,47 @@ __device__ __forceinline__ void ep_block(const uint32_t (&re)[16], const uint32_
     p1 += a + b;
 }
 
+// Tail of a call whose last tile is partial (see the state code of the drain warps): out of line, so that its registers (two
+// blocks of f pieces, the double recursion) do not count against the kernel's hot loops.
+__device__ __noinline__ void tc_partial_tail(uint32_t taddr_a, uint32_t taddr_b, uint32_t taddr_state, double wi0, double wi1, double wi2,
+                                             double wi3, double b0, double b1, double b2, double a1, double a2, double g_bq, float isig,
+                                             int row0, int last_frames, float *yhist_next, double *bq_state_next, int C)
+{
+    using namespace tc;
+    uint32_t fa[16], fb[16], ws[2];
+    tmem_ld16(taddr_a, fa);
+    tmem_ld16(taddr_b, fb);
+    // the block's true state, as this warp has just written it to the mailbox (balanced coordinates) -> TDF-II basis
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(ws[0]), "=r"(ws[1]) : "r"(taddr_state));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const double w0d = (double)__uint_as_float(ws[0]), w1d = (double)__uint_as_float(ws[1]);
+    double S0 = fma(wi0, w0d, wi1 * w1d), S1 = fma(wi2, w0d, wi3 * w1d);
+    const double na1 = -a1, na2 = -a2;
+    const int nrows = last_frames + kTcHr - row0;   // rows row0 .. last_frames + 14
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        if (k < nrows) {
+            const uint32_t w0 = k < 16 ? fa[k >> 1] : fb[(k - 16) >> 1], w1 = k < 16 ? fa[8 + (k >> 1)] : fb[8 + ((k - 16) >> 1)];
+            const __half2 h0 = *reinterpret_cast<const __half2 *>(&w0), h1 = *reinterpret_cast<const __half2 *>(&w1);
+            const float fg = (k & 1) ? __high2float(h0) + __high2float(h1) : __low2float(h0) + __low2float(h1);
+            const double x = (double)(fg * isig);
+            const double v = fma(b0, x, S0);
+            const double tt = fma(b1, x, S1);
+            S0 = fma(na1, v, tt);
+            S1 = fma(na2, v, b2 * x);
+            const int hr = row0 + k - last_frames;   // 0..14: position in the carried history
+            if (hr >= 0) yhist_next[(size_t)hr * C] = (float)(v * g_bq);
+        }
+    }
+    bq_state_next[0] = S0;
+    bq_state_next[1] = S1;
+}
+
 // PROF: 1 = per-role cycle counters (PB_TC_PROF=1; a compile-time switch: the counters cost the issue loops dearly, ~6 k cycles
 // per tile), 2 = event timeline of CTA 0 only (PB_TC_PROF=2; nearly free)
-template <int PROF>
+// PARTIAL: the call's last tile may hold fewer than 160 frames (a separate instantiation: the few extra instructions in the output
+// and drain warps cost a whole-tile batch 6 %, measured -- this kernel is that sensitive to its register allocation).
+template <int PROF, bool PARTIAL = false>
 __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_constant__ TcParams p)
 {
     using namespace tc;
@@ -703,11 +744,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             if (!(p.dbg & 32)) tmem_st16(tmem_base + lane_base + kColA1 + 16 * st, hi, lo);   // x0: 8 columns, x1: 8 columns
             if (last) {
                 // carried FIR input history: frames [n-hist_rows, n) in gain-scaled units (K1's convention)
-                const int hrow0 = 16 * q - (kTcWin - p.hist_rows);
-                if (hrow0 + 15 >= 0) {
+                // (the window ends kTcFrames - last_frames rows behind the call's last frame when the last tile is partial)
+                const int hrow0 = 16 * q - (kTcLead + (PARTIAL ? p.last_frames : kTcFrames) - p.hist_rows);
+                if (hrow0 + 15 >= 0 && hrow0 < p.hist_rows) {
 #pragma unroll
                     for (int i = 0; i < 16; i++)
-                        if (hrow0 + i >= 0) p.xhist_next[(size_t)(hrow0 + i) * p.C + c] = v[i] * gsc;
+                        if (hrow0 + i >= 0 && hrow0 + i < p.hist_rows) p.xhist_next[(size_t)(hrow0 + i) * p.C + c] = v[i] * gsc;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&raw_empty[st]);
@@ -931,6 +973,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             if (gl) PB_TRACE(4, it, 12);   // look-back done
             // ---- true state at the start of every block = zero-state part (role A, in the mailbox) + response to the incoming state
             double s10_1, s10_2;
+            const int end_blk = (PARTIAL && last && p.last_frames < kTcFrames) ? p.last_frames >> 4 : -1;   // block of tile row `last_frames`
             {
                 const float qf0 = d2f_bits(fma(p.Wb[0], q1, p.Wb[1] * q2)), qf1 = d2f_bits(fma(p.Wb[2], q1, p.Wb[3] * q2));
                 const int fi = first ? 1 : 0;
@@ -968,6 +1011,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 p.lb_inc[slot * 64 + lane * 2 + 1] = I1;
                 __syncwarp();
                 if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbInc);
+            } else if (PARTIAL && end_blk >= 0) {
+                // Partial last tile: the call ends after tile row 14 + last_frames (row = frame + 15).  Carried biquad state (after
+                // that row) and carried y history (its last 15 rows) by running the recursion row by row from the true state at
+                // the start of the block that holds row `last_frames` -- a float in balanced coordinates, like every block state
+                // (6e-8 of the state; the full-tile case below starts from the double inclusive state) -- over the pieces of f in
+                // that block's and the next block's E columns: at most 30 rows.
+                tc_partial_tail(tmem_base + lane_base + kColE + 16 * end_blk,
+                                tmem_base + lane_base + kColE + 16 * (end_blk + 1 < kTcBlocks ? end_blk + 1 : end_blk),
+                                tmem_base + lane_base + kColMbox + 2 * end_blk, p.Wbi[0], p.Wbi[1], p.Wbi[2], p.Wbi[3],
+                                p.b0, p.b1, p.b2, p.a1, p.a2, p.g_bq, isig, 16 * end_blk, p.last_frames, p.yhist_next + c,
+                                p.bq_state_next + 2 * c, p.C);
             } else {
                 // carried biquad state (after row 174) and carried y history (rows 160..174): the only place where the
                 // recursion runs row by row, from the pieces of f that role A wrote over block 10's E columns
@@ -1014,7 +1068,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         unsigned nsl = 0;  // running slice number: phase of the D2 barriers
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
-            const bool first = (t == 0);
+            const bool first = (t == 0), part_tile = PARTIAL && (t == p.n_tiles - 1) && p.last_frames < kTcFrames;
             const int c = cg * kTcCh + e * 32 + lane;
             const uint32_t par = it & 1;
             float *outp = p.out + (size_t)t * kTcOut * p.C + c;
@@ -1061,7 +1115,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             r_w += k9 - k8;
             if (warp == 18) PB_TRACE(6, it, 8);
             // 16 outputs of slice s from their sums: descale, block-state correction, store, meter
-            auto emit = [&](int s, auto sum_of) {
+            auto emit = [&](int s, auto sum_of, auto partial) {
                 // true state at the start of the four blocks this slice reads
                 uint32_t zs[8];
                 tmem_ld8(tmem_base + lane_base + kColMbox + 4 * s, zs);
@@ -1073,7 +1127,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 }
                 const f32x2 sb01 = pk2(__uint_as_float(zs[0]), __uint_as_float(zs[1])), sb23 = pk2(__uint_as_float(zs[2]), __uint_as_float(zs[3]));
                 const f32x2 sb45 = pk2(__uint_as_float(zs[4]), __uint_as_float(zs[5])), sb67 = pk2(__uint_as_float(zs[6]), __uint_as_float(zs[7]));
-                const int nout = ((s == kRsSlices - 1) ? kTcOut - kRsN * (kRsSlices - 1) : kRsN) - 16 * hsel;
+                // (a partial last tile stores only the outputs its frames have triggered)
+                // (PARTIAL: the call's last tile when it is not full -- it stores only the outputs its frames have triggered; a
+                // separate instantiation, so that the loop of every other tile keeps its two possible trip counts)
+                const int nout = (decltype(partial)::value ? p.last_outputs - kRsN * s : (s == kRsSlices - 1) ? kTcOut - kRsN * (kRsSlices - 1) : kRsN) - 16 * hsel;
                 const float *rcg = rcs + (size_t)(((first && s == 0) ? kTcRcFirst : kRsN * s) + 16 * hsel) * 8;
                 float *op = outp + (size_t)(kRsN * s + 16 * hsel) * p.C;
 #pragma unroll
@@ -1099,9 +1156,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
 #pragma unroll 1
             for (int s = 0; s < kRsSlices - 1; s++) {
                 const float *pp = park + (size_t)(kRsN * s) * kTcCh;
-                emit(s, [&](int i) { return pp[i * kTcCh]; });
+                if (PARTIAL && part_tile) emit(s, [&](int i) { return pp[i * kTcCh]; }, std::integral_constant<bool, PARTIAL>{});
+                else emit(s, [&](int i) { return pp[i * kTcCh]; }, std::false_type{});
             }
-            emit(kRsSlices - 1, [&](int i) { return hold[i]; });
+            if (PARTIAL && part_tile) emit(kRsSlices - 1, [&](int i) { return hold[i]; }, std::integral_constant<bool, PARTIAL>{});
+            else emit(kRsSlices - 1, [&](int i) { return hold[i]; }, std::false_type{});
             o_out += (PROF == 1 ? clk() : 0ll) - k9;
             if (warp == 18) PB_TRACE(6, it, 9);
             r_m += (PROF == 1 ? clk() : 0ll) - k5;

@@ -358,8 +358,8 @@ def test_k2_tensor_path_matches_oracle(channels, bf, nb):
 
 
 def test_k2_and_k1_share_carried_state():
-    # calls that do not start and end on K2's 160-frame grid are cut into a K1 head, a K2 middle and a K1 tail; calls with less
-    # than one aligned tile run on K1 alone; history, biquad state and resampler phase must carry across every hand-over
+    # calls of at least one 160-frame tile run on K2 from their first frame at whatever resampler phase they start (last tile
+    # partial), shorter calls on K1 alone; history, biquad state and resampler phase must carry across every hand-over
     ch = 128
     gpu, cpu = _k2_chain(ch, 1600, 1), orc.Chain(ch, design.config_stages("chain4"))
     paths = []
@@ -723,22 +723,56 @@ def test_k3_two_sweeps_with_few_channel_groups(dtype, channels):
     d_out.free()
 
 
-def test_k2_serves_4096_frame_buffers_between_k1_head_and_tail():
-    # bufferSize 4096 is not a multiple of K2's 160-frame tile and the resampler phase returns to 0 only every fifth buffer:
-    # every call is cut into a K1 head (to the next multiple of 160 in the stream), a K2 middle and a K1 tail.  Bit-exact frame
-    # counts (3763, 3763, 3763, 3763, 3764, ...) and the 1e-6 bar on every buffer.
+def test_k2_serves_one_4096_frame_buffer_per_call_in_one_launch():
+    # bufferSize 4096 is not a multiple of K2's 160-frame tile and the resampler phase at the start of a buffer returns to 0 only
+    # every fifth buffer.  The tiles of a call start at its first frame with the tables of the phase found there (160 frames give
+    # 147 outputs from any phase) and the last tile is partial (96 frames: rows behind them zero-filled, outputs masked, carried
+    # state taken at the last real row): every call is ONE K2 launch plus its verify launch, no K1 head or tail.  Bit-exact
+    # frame counts (3763, 3763, 3763, 3763, 3764, ...) and the 1e-6 bar on every buffer.
     ch, bf = 128, 4096
     st = design.config_stages("chain4")
     gpu, cpu = abi.Chain(ch, st, buffer_frames=bf), orc.Chain(ch, st)
-    lens = []
-    for b in range(6):
+    lens, launches = [], 0
+    for b in range(11):
         x = signal_input(bf, ch, seed=30 + b)
         ref = cpu.process(x)
         y = gpu.process(x.astype(np.float32))
         lens.append(len(y))
-        assert gpu.last_path()[0] == 2
+        path, n_launch = gpu.last_path()
+        assert path == 2 and n_launch - launches == 2, (path, n_launch - launches)
+        launches = n_launch
         assert_parity(y, ref, REL_F32, f"buffer {b}")
-    assert lens == [3763, 3763, 3763, 3763, 3764, 3763]
+    assert lens == [3763, 3763, 3763, 3763, 3764, 3763, 3763, 3763, 3763, 3764, 3763]
+
+
+@pytest.mark.parametrize("channels", [128, 384])
+def test_k2_partial_last_tile_at_every_kind_of_boundary(channels):
+    # Call lengths that leave 1, 15, 16, 17, 159 ... frames in the last tile, end exactly on a tile boundary, are shorter than one
+    # tile (K1 serves those, from the state K2 left, and K2 continues from K1's), with the fused meter: every call against
+    # the oracle, frame counts bit-exact, and the meter over the whole stream.
+    st = design.config_stages("chain4")
+    sizes = [161, 175, 176, 177, 319, 320, 4096, 159, 1, 160, 2000, 4095, 33, 1600, 4000, 4001]
+    bf = max(sizes)
+    gpu, cpu = abi.Chain(channels, st, buffer_frames=bf, flags=abi.CHAIN_METER), orc.Chain(channels, st)
+    x = signal_input(sum(sizes), channels, seed=77)
+    pos, refs, run_peak = 0, [], np.zeros(channels)
+    for i, n in enumerate(sizes):
+        blk = x[pos:pos + n]
+        pos += n
+        ref = cpu.process(blk)
+        refs.append(ref)
+        if len(ref):
+            run_peak = np.maximum(run_peak, np.abs(ref).max(axis=0))
+        assert gpu.peek_out_frames(n) == len(ref)
+        y = gpu.process(blk.astype(np.float32))
+        assert len(y) == len(ref), f"call {i} ({n} frames): {len(y)} vs {len(ref)} frames"
+        assert gpu.last_path()[0] == (2 if n >= 160 else 1), (n, gpu.last_path())
+        assert_parity(y, ref, REL_F32, f"call {i} ({n} frames)", floor=run_peak)
+    peak, sumsq, frames = gpu.meter_read()
+    rp, rs = orc.meter(np.concatenate(refs))
+    assert frames == sum(len(r) for r in refs)
+    np.testing.assert_allclose(peak, rp, rtol=2e-6)
+    np.testing.assert_allclose(sumsq, rs, rtol=2e-6)
 
 
 # ------------------------------------------------ graph edits: InsertProcessor on a fused run (pipe.go:297-333) --

@@ -1,6 +1,6 @@
 """Device-resident throughput of configs[2] when the caller hands over ONE 4096-frame buffer per call (what the reference's
-ProcessFunc does, pipe.go:438) instead of a batch.  4096 is not a multiple of K2's 160-frame tile: every call is a K1 head,
-a K2 middle and a K1 tail.  Run on a GPU box:  python tools/per_buffer.py"""
+ProcessFunc does, pipe.go:438) instead of a batch.  4096 is not a multiple of K2's 160-frame tile: the tiles of a call start at
+its first frame (per-phase tables) and the last tile is partial -- one K2 launch plus its verify launch per call (PB_TC_TAIL_K1=1: whole tiles on K2, the rest on K1, as before).  Run on a GPU box:  python tools/per_buffer.py"""
 import os
 import sys
 
@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 from pipe_b200 import abi, design  # noqa: E402
 
 ch, bf, nbuf = 1024, 4096, 40
-for flags, name in ((0, "split K1 | K2 | K1"), (abi.CHAIN_NO_TENSOR, "K1 only (PB_CHAIN_NO_TENSOR)")):
+for flags, name in ((0, "K2, one launch per call"), (abi.CHAIN_NO_TENSOR, "K1 only (PB_CHAIN_NO_TENSOR)")):
     chain = abi.Chain(ch, design.config_stages("chain4"), buffer_frames=bf, flags=flags)
     x = torch.empty((bf * nbuf, ch), dtype=torch.float32, device="cuda:0")
     y = torch.empty((bf, ch), dtype=torch.float32, device="cuda:0")
