@@ -331,7 +331,7 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s, int acc0 = 0, Segment::T
     auto rtap = [&](int row, int m) -> double {
         if (m >= kTcOut || row < 0 || row >= kTcN) return 0.0;
         // the integer accumulator starts the tile at acc0: after tile frame i it has seen acc0 + 147 (i + 1), output m leaves at
-        // the first i where that reaches 160 (m + 1), with what is left over as the accumulator (pipe_oracle.c, resampler)
+        // the first i where that reaches 160 (m + 1), with what is left over as the accumulator (resampler)
         const int im = (kTcFrames * (m + 1) - acc0 + kTcUp - 1) / kTcUp - 1;
         const int k = im + kTcHr - row;
         if (k < 0 || k >= kTcP) return 0.0;
