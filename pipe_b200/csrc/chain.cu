@@ -75,7 +75,7 @@ struct Segment {
     std::map<int, TcPhase> tc_phase;
     // K3 (streaming kernels): runs without FIR and without resampler
     bool st_ok = false;
-    int st_grid = 0;
+    int st_grid = 0, st_agg_grid = 0;
     void *d_st_tab = nullptr;                        // StTab
     void *d_scan_blk = nullptr;                      // K3 two sweeps: block aggregates of the scan [groups][kScanBlocks][32][2] doubles
     double st_wt[32][2] = {};                        // A^k B, passed in the kernel parameters
@@ -234,6 +234,11 @@ template <typename T>
 static cudaError_t configure_stream_kernels(int *per_sm)
 {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, chain_stream_kernel<T, 0, kStOneSweep>, kStThreads, 0);
+}
+template <typename T>
+static cudaError_t configure_aggregate_kernel(int *per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, stream_aggregate_kernel<T, 0>, kStThreads, 0);
 }
 
 // one launch of chain_stream_kernel in the given mode; the channel counts of BASELINE.json's configs get row addresses with
@@ -896,6 +901,10 @@ static int32_t build_segment(pb_chain *c, Segment &s)
         else PB_CUDA((configure_stream_kernels<double>(&per_sm)));
         if (per_sm < 1) return fail(PB_ERR_UNSUPPORTED, "streaming kernel does not fit on an SM");
         s.st_grid = per_sm * c->num_sms;
+        int agg_per_sm = 0;
+        if (f32) PB_CUDA((configure_aggregate_kernel<float>(&agg_per_sm)));
+        else PB_CUDA((configure_aggregate_kernel<double>(&agg_per_sm)));
+        s.st_agg_grid = std::max(1, agg_per_sm) * c->num_sms;
     }
     // tables
     if (has_fir) PB_CUDA(cudaMalloc(&s.d_taps, el * (size_t)s.tp_len));
@@ -904,7 +913,12 @@ static int32_t build_segment(pb_chain *c, Segment &s)
         PB_CUDA(cudaMalloc(&s.d_wt, sizeof(double) * (size_t)s.wt_len * 2));
         s.lb_tiles = (int)ceil_div64(c->max_frames, std::min(s.L, s.st_ok ? kStMinTile : kTcFrames)) + 1;
         if (s.st_ok) PB_CUDA(cudaMalloc(&s.d_st_tab, sizeof(double) * (size_t)StTab::kCount));
-        if (s.st_ok) PB_CUDA(cudaMalloc(&s.d_scan_blk, sizeof(double) * 64 * (size_t)kScanBlocks * ((size_t)(c->C + kCg - 1) / kCg)));
+        if (s.st_ok) {   // block aggregates of the scan, and behind them one flag word per block (the epoch that wrote it)
+            const size_t blk_bytes = sizeof(double) * 64 * (size_t)kScanBlocks * ((size_t)(c->C + kCg - 1) / kCg);
+            const size_t flag_bytes = sizeof(unsigned) * (size_t)kScanBlocks * ((size_t)(c->C + kCg - 1) / kCg);
+            PB_CUDA(cudaMalloc(&s.d_scan_blk, blk_bytes + flag_bytes));
+            PB_CUDA(cudaMemset(s.d_scan_blk, 0, blk_bytes + flag_bytes));
+        }
         const size_t groups = (size_t)(c->C + kCg - 1) / kCg;
         PB_CUDA(cudaMalloc(&s.d_agg, sizeof(double) * groups * s.lb_tiles * 64));
         PB_CUDA(cudaMalloc(&s.d_inc, sizeof(double) * groups * s.lb_tiles * 64));
@@ -1071,28 +1085,32 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
     // With few channel groups hundreds of tiles of one group are in flight and the look-back of a single sweep is what the launch
     // waits for: two sweeps with a scan in between instead (chain_stream.cuh, kStOneSweep).  PB_ST_TWO_SWEEPS=<groups> moves the
     // threshold (0: never), for measurements.
-    static const int two_sweep_groups = getenv("PB_ST_TWO_SWEEPS") ? atoi(getenv("PB_ST_TWO_SWEEPS")) : 4;
+    // (at most 8 groups: the scan's n_groups x kScanBlocks CTAs wait for each other and must be co-resident)
+    static const int two_sweep_groups = std::min(8, getenv("PB_ST_TWO_SWEEPS") ? atoi(getenv("PB_ST_TWO_SWEEPS")) : 4);
     if (has_bq && p.n_groups <= two_sweep_groups && p.n_tiles >= 256) {
-        launch_stream_mode<T, kStAggregate>(p, grid, c->C, stream);
+        // neither sweep draws tickets (static tile schedules), so the chain's ticket counter does not move
+        const int agg_grid = (int)std::min<int64_t>((int64_t)(p.n_tiles - 1) * p.n_groups, (int64_t)s.st_agg_grid);
+        if (c->C == 64) stream_aggregate_kernel<T, 64><<<agg_grid, kStThreads, 0, stream>>>(p);
+        else if (c->C == 256) stream_aggregate_kernel<T, 256><<<agg_grid, kStThreads, 0, stream>>>(p);
+        else stream_aggregate_kernel<T, 0><<<agg_grid, kStThreads, 0, stream>>>(p);
         PB_CUDA(cudaGetLastError());
-        c->ticket_base += (unsigned long long)total + (unsigned long long)grid * kStTicketsPerCta;
-        p.ticket_base = c->ticket_base;
         // block aggregates: the first kScanBlocks slots of the (otherwise unused) inclusive-state array of the LAST tile row would
         // alias live data, so they have their own scratch behind the look-back arrays
         const dim3 sgrid((unsigned)p.n_groups, (unsigned)kScanBlocks);
-        stream_scan_kernel<0><<<sgrid, kScanWarps * 32, 0, stream>>>(p.lb_agg, p.lb_inc, (double *)s.d_scan_blk, p.bq_state, p.tab, c->C,
-                                                                     p.n_tiles, p.n_tiles - 1);
-        stream_scan_kernel<1><<<sgrid, kScanWarps * 32, 0, stream>>>(p.lb_agg, p.lb_inc, (double *)s.d_scan_blk, p.bq_state, p.tab, c->C,
-                                                                     p.n_tiles, p.n_tiles - 1);
+        const size_t blk_doubles = 64 * (size_t)kScanBlocks * (size_t)p.n_groups;
+        stream_scan_kernel<<<sgrid, kScanWarps * 32, 0, stream>>>(p.lb_agg, p.lb_inc, (double *)s.d_scan_blk,
+                                                                  reinterpret_cast<unsigned *>((double *)s.d_scan_blk + blk_doubles), p.bq_state,
+                                                                  p.tab, c->C, p.n_tiles, p.n_tiles - 1, p.epoch, p.err_flag);
         PB_CUDA(cudaGetLastError());
         launch_stream_mode<T, kStApply>(p, grid, c->C, stream);
+        PB_CUDA(cudaGetLastError());
         c->launches += 3;
     } else {
         launch_stream_mode<T, kStOneSweep>(p, grid, c->C, stream);
+        PB_CUDA(cudaGetLastError());
+        c->ticket_base += (unsigned long long)total + (unsigned long long)grid * kStTicketsPerCta;
+        c->launches++;
     }
-    PB_CUDA(cudaGetLastError());
-    c->ticket_base += (unsigned long long)total + (unsigned long long)grid * kStTicketsPerCta;
-    c->launches++;
     if (has_bq) s.pp ^= 1;
     return PB_OK;
 }

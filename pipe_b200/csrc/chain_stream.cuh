@@ -50,12 +50,12 @@ namespace pb {
 // How the tiles of a launch learn their incoming biquad state:
 //   kStOneSweep   decoupled look-back inside one launch (8 B of HBM traffic per f32 sample).  Right when there are many channel
 //                 groups: the tiles in flight spread over them and the walk is short (1024 ch: 65 % of the HBM peak).
-//   kStAggregate + stream_scan_kernel + kStApply ("two sweeps")   with FEW channel groups (configs[1]: 64 ch = 2 groups) hundreds
+//   stream_aggregate_kernel + stream_scan_kernel + kStApply ("two sweeps")   with FEW channel groups (configs[1]: 64 ch = 2 groups) hundreds
 //                 of tiles of one group are in flight, every tile folds up to 256 predecessors and the launch sits at 33 % of the
 //                 peak waiting for them.  Reading the input twice costs 12 B per sample but nothing ever waits: sweep 1 stores
 //                 every tile's aggregate, a one-CTA-per-group scan turns them into inclusive states, sweep 2 (in REVERSE tile
 //                 order: the end of the batch is what sweep 1 left in L2) runs the recursion from the resolved states.
-enum : int { kStOneSweep = 0, kStAggregate = 1, kStApply = 2 };
+enum : int { kStOneSweep = 0, kStApply = 2 };
 constexpr int kStTicketsPerCta = 1;  // tickets a CTA draws past the end of the batch
 constexpr int kStThreads = 256;
 constexpr int kStWarps = kStThreads / 32;        // 8 sub-chunks per tile, and 8 look-back windows
@@ -256,14 +256,22 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
         for (int i = tid; i < StTab::kCount; i += kStThreads) tab_s[i] = p.tab[i];
     const double *pw_s = tab_s + StTab::kPw, *lb_s = tab_s + StTab::kLb, *mw_s = tab_s + StTab::kMw;
 
-    for (;;) {
+    for (int it = 0;; it++) {
         __syncthreads();  // previous tile done with shared memory (and the tables visible)
-        if (tid == 0) s_tile = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-        __syncthreads();
-        if (s_tile >= total_tiles) break;
         // One sweep: time-major tickets -- a tile only waits on smaller tickets, which resident CTAs already hold.  Second of two
-        // sweeps: nothing waits, and the batch is walked backwards (see kStApply).
-        const int tile = MODE == kStApply ? total_tiles - 1 - s_tile : s_tile;
+        // sweeps: nothing waits, so the tiles are dealt out statically (a ticket is an atomic round trip in front of every tile's
+        // loads) and the batch is walked backwards (see kStApply).
+        int tile;
+        if (MODE == kStApply) {
+            const int k = (int)blockIdx.x + it * (int)gridDim.x;
+            if (k >= total_tiles) break;
+            tile = total_tiles - 1 - k;
+        } else {
+            if (tid == 0) s_tile = (int)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+            __syncthreads();
+            if (s_tile >= total_tiles) break;
+            tile = s_tile;
+        }
         T *xs_w = xs + warp * R * kCg;
         st_issue_tile<T>(p, C, tile, xs_w, warp, lane);
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -316,20 +324,14 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
                     const double2 z = *reinterpret_cast<const double2 *>(zq_s + (q * kCg + lane) * 2);
                     mat2_fma(pw_s + 4 * (kStWarps - 1 - q), z.x, z.y, Z0, Z1);
                 }
-                if (MODE == kStAggregate) {
-                    // first of two sweeps: the aggregate is all this launch wants from the tile (the scan reads full tiles only)
+                *reinterpret_cast<double2 *>(zsum_s + lane * 2) = make_double2(Z0, Z1);
+                if (!last && !first) {
+                    // payload by every lane, then ONE release by lane 0: the warp barrier orders the lanes' stores before it
                     *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
-                } else {
-                    *reinterpret_cast<double2 *>(zsum_s + lane * 2) = make_double2(Z0, Z1);
-                    if (!last && !first) {
-                        // payload by every lane, then ONE release by lane 0: the warp barrier orders the lanes' stores before it
-                        *reinterpret_cast<double2 *>(p.lb_agg + slot * 64 + lane * 2) = make_double2(Z0, Z1);
-                        __syncwarp();
-                        if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
-                    }
+                    __syncwarp();
+                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
                 }
             }
-            if (MODE == kStAggregate) continue;
             double S0 = 0.0, S1 = 0.0;  // incoming state of the tile
             if (MODE == kStApply) {
                 // the scan left the inclusive state after every full tile in lb_inc
@@ -468,12 +470,76 @@ __global__ void __launch_bounds__(kStThreads, PB_ST_MINB) chain_stream_kernel(co
     }
 }
 
+// First of two sweeps: the aggregate (zero-state end state) of every full tile in front of the last one, and nothing else.  No
+// tickets, no shared-memory staging: the R rows of a warp go from HBM straight into registers -- one 128 B line per row and warp,
+// all R loads in flight before the first is used --, 2 DFMA per sample give the sub-chunk's end state, and the eight sub-chunk
+// states of a tile are combined by one warp (a different one every tile, so that no warp is the slow one).  Tiles are dealt
+// round-robin, tile = CTA + k * grid: the resident CTAs read one contiguous window of the batch.  (Measured alternatives, slower:
+// one contiguous share of the batch per CTA, chaining the tile aggregates on the way -- 67 us against 57: hundreds of concurrent
+// streams --; segments of 2..16 consecutive tiles per CTA -- 67-72 us.)
+template <typename T, int CC>
+__global__ void __launch_bounds__(kStThreads, 4) stream_aggregate_kernel(const __grid_constant__ StreamParams<T> p)
+{
+    constexpr int R = StShape<T>::kRows, kTile = StShape<T>::kTile;
+    __shared__ double pw_s[4 * kStWarps];
+    __shared__ __align__(16) double wt_s[32][2];   // A^k B from shared memory: as kernel parameters the compiler hoists all 64 out of the
+                                                   // tile loop and spills them
+    __shared__ __align__(16) double zq_s[2][kStWarps * kCg * 2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = CC ? CC : p.C;
+    const int64_t ld = C;
+    if (tid < 4 * kStWarps) pw_s[tid] = p.tab[StTab::kPw + tid];
+    if (tid >= 64 && tid < 128) wt_s[(tid - 64) >> 1][tid & 1] = p.wt[(tid - 64) >> 1][tid & 1];
+    __syncthreads();
+    const int total = (p.n_tiles - 1) * p.n_groups;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+        const int t = tile / p.n_groups, g = tile - t * p.n_groups;
+        const int c = g * kCg + lane;
+        const bool cvalid = c < C;
+        const T *src = p.in + ((int64_t)t * kTile + warp * R) * ld + (cvalid ? c : 0);
+        T x[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) x[i] = cvalid ? __ldg(src + i * ld) : T(0);
+        double z0 = 0.0, z1 = 0.0, y0 = 0.0, y1 = 0.0, u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < R; i += 4) {
+            // (conversions pinned in program order: hoisted in front of the loop they keep 32 doubles alive and spill)
+            const double xa = to_double_again(x[i]), xb = to_double_again(x[i + 1]), xc = to_double_again(x[i + 2]), xd = to_double_again(x[i + 3]);
+            const double2 wa = *reinterpret_cast<const double2 *>(wt_s[R - 1 - i]), wb = *reinterpret_cast<const double2 *>(wt_s[R - 2 - i]);
+            const double2 wc = *reinterpret_cast<const double2 *>(wt_s[R - 3 - i]), wd = *reinterpret_cast<const double2 *>(wt_s[R - 4 - i]);
+            z0 = fma(wa.x, xa, z0);
+            z1 = fma(wa.y, xa, z1);
+            y0 = fma(wb.x, xb, y0);
+            y1 = fma(wb.y, xb, y1);
+            u0 = fma(wc.x, xc, u0);
+            u1 = fma(wc.y, xc, u1);
+            v0 = fma(wd.x, xd, v0);
+            v1 = fma(wd.y, xd, v1);
+        }
+        double *zq = zq_s[it & 1];   // two buffers: the combining warp may still be reading the previous tile's
+        *reinterpret_cast<double2 *>(zq + (warp * kCg + lane) * 2) = make_double2((z0 + y0) + (u0 + v0), (z1 + y1) + (u1 + v1));
+        __syncthreads();
+        if (warp == (it & (kStWarps - 1))) {
+            double Z0 = 0.0, Z1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < kStWarps; q++) {
+                const double2 z = *reinterpret_cast<const double2 *>(zq + (q * kCg + lane) * 2);
+                mat2_fma(pw_s + 4 * (kStWarps - 1 - q), z.x, z.y, Z0, Z1);
+            }
+            *reinterpret_cast<double2 *>(p.lb_agg + ((size_t)g * p.n_tiles + t) * 64 + lane * 2) = make_double2(Z0, Z1);
+        }
+    }
+}
+
 // Between the two sweeps: inclusive state after every full tile, S_t = (A^T) S_{t-1} + Z_t.  A dependent DFMA costs ~100 cycles
 // on this part, so the recursion is cut three ways until no chain is long: the tiles of a channel group into kScanBlocks blocks
-// (one CTA each), a block into 32 segments (one warp each, lane = channel).  PHASE 0: segment aggregates by Horner, prefix over
-// the block's segments from a zero state, block aggregate to global memory.  PHASE 1: the block's start state from the carried
-// state and the aggregates of the blocks in front, the same prefix from it, then every warp walks its segment again and stores
-// the inclusive states.  Payloads (L2, ~700 cycles) are fetched a batch ahead of the recursion.
+// (one CTA each), a block into 32 segments (one warp each, lane = channel).  First: segment aggregates by Horner, prefix over
+// the block's segments from a zero state, block aggregate to global memory.  Then: the block's start state from the carried
+// state and the aggregates of the blocks in front, the same prefix from it, and every warp walks its segment again and stores
+// the inclusive states.  Payloads (L2) are fetched a batch ahead of the recursion.  (These warps are single dependent chains at
+// ~20 cycles per instruction: the launch takes ~15 us whatever its arithmetic; a scan over per-CTA segments instead of tiles
+// measured the same.)
 constexpr int kScanWarps = 32, kScanBatch = 4, kScanBlocks = 16;
 template <bool STORE>
 __device__ __forceinline__ void scan_walk(const double *agg_g, double *inc_g, int t0, int t1, double m0, double m1, double m2, double m3,
@@ -521,11 +587,15 @@ __device__ __forceinline__ void mat2_pow(const double (&M)[4], int e, double (&P
         B[0] = q0; B[1] = q1; B[2] = q2; B[3] = q3;
     }
 }
-// blk: [n_groups][kScanBlocks][32 lanes][2] block aggregates (scratch in global memory)
-template <int PHASE>
+// blk: [n_groups][kScanBlocks][32 lanes][2] block aggregates (scratch in global memory); flags: [n_groups][kScanBlocks] words, the
+// epoch of the launch that wrote the block aggregate (release / acquire).  ONE launch of n_groups x kScanBlocks CTAs (at most 128
+// with the four channel groups two sweeps serve: always co-resident, so a CTA may wait for the CTAs in front of it): every CTA
+// publishes its block aggregate as soon as it has it and then waits only for the blocks IN FRONT of it, whose aggregates depend
+// on nothing.
 __global__ void __launch_bounds__(kScanWarps * 32) stream_scan_kernel(const double *__restrict__ agg, double *__restrict__ inc,
-                                                                      double *__restrict__ blk, const double *__restrict__ bq_state,
-                                                                      const double *__restrict__ tab, int C, int n_tiles, int n_full)
+                                                                      double *__restrict__ blk, unsigned *__restrict__ flags,
+                                                                      const double *__restrict__ bq_state, const double *__restrict__ tab,
+                                                                      int C, int n_tiles, int n_full, unsigned epoch, int *err_flag)
 {
     __shared__ double seg_s[kScanWarps][kCg][2];
     __shared__ double start_s[kScanWarps][kCg][2];
@@ -540,6 +610,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) stream_scan_kernel(const doub
     const double *agg_g = agg + (size_t)g * n_tiles * 64 + lane * 2;
     double *inc_g = inc + (size_t)g * n_tiles * 64 + lane * 2;
     double *blk_g = blk + ((size_t)g * kScanBlocks) * 64 + lane * 2;
+    unsigned *flag_g = flags + (size_t)g * kScanBlocks;
     double a0 = 0.0, a1 = 0.0;
     scan_walk<false>(agg_g, inc_g, t0, t1, M[0], M[1], M[2], M[3], a0, a1);
     seg_s[w][lane][0] = a0;
@@ -548,35 +619,61 @@ __global__ void __launch_bounds__(kScanWarps * 32) stream_scan_kernel(const doub
     if (w == 0) {
         double P[4];
         mat2_pow(M, per, P);
-        double s0 = 0.0, s1 = 0.0;
-        if (PHASE == 1) {
-            // start state of the block: the carried state through the blocks in front (every block in front of this one is full)
-            double Q[4];
-            mat2_pow(M, span, Q);
-            s0 = c < C ? bq_state[2 * c] : 0.0;
-            s1 = c < C ? bq_state[2 * c + 1] : 0.0;
-            for (int k = 0; k < b; k++) {
-                const double2 z = __ldcg(reinterpret_cast<const double2 *>(blk_g + (size_t)k * 64));
-                const double n0 = fma(Q[0], s0, fma(Q[1], s1, z.x)), n1 = fma(Q[2], s0, fma(Q[3], s1, z.y));
+        // the prefix over the block's segments: from a zero state (-> block aggregate), then again from the block's start state
+        auto prefix = [&](double s0, double s1, bool keep) {
+            for (int k = 0; k < kScanWarps; k++) {
+                if (keep) {
+                    start_s[k][lane][0] = s0;
+                    start_s[k][lane][1] = s1;
+                }
+                // the step over segment k: A^T to the number of tiles it holds (`per`, fewer in the block's last segment, none behind it)
+                const int left = b1 - (b0 + k * per), nk = left < 0 ? 0 : (left > per ? per : left);
+                if (nk == 0) continue;
+                double R[4] = {P[0], P[1], P[2], P[3]};
+                if (nk != per) mat2_pow(M, nk, R);
+                const double n0 = fma(R[0], s0, fma(R[1], s1, seg_s[k][lane][0])), n1 = fma(R[2], s0, fma(R[3], s1, seg_s[k][lane][1]));
                 s0 = n0;
                 s1 = n1;
             }
+            return make_double2(s0, s1);
+        };
+        if (b + 1 < kScanBlocks) {   // nobody is behind the last block
+            const double2 z = prefix(0.0, 0.0, false);
+            *reinterpret_cast<double2 *>(blk_g + (size_t)b * 64) = z;
+            __syncwarp();
+            if (lane == 0) st_release_u32(flag_g + b, epoch);
         }
-        for (int k = 0; k < kScanWarps; k++) {
-            start_s[k][lane][0] = s0;
-            start_s[k][lane][1] = s1;
-            // the step over segment k: A^T to the number of tiles it holds (`per`, fewer in the block's last segment, none behind it)
-            const int left = b1 - (b0 + k * per), nk = left < 0 ? 0 : (left > per ? per : left);
-            if (nk == 0) continue;
-            double R[4] = {P[0], P[1], P[2], P[3]};
-            if (nk != per) mat2_pow(M, nk, R);
-            const double n0 = fma(R[0], s0, fma(R[1], s1, seg_s[k][lane][0])), n1 = fma(R[2], s0, fma(R[3], s1, seg_s[k][lane][1]));
-            s0 = n0;
-            s1 = n1;
+        // start state of the block: the carried state through the blocks in front (every block in front of this one is full)
+        double s0 = c < C ? bq_state[2 * c] : 0.0, s1 = c < C ? bq_state[2 * c + 1] : 0.0;
+        if (b > 0) {
+            for (unsigned spins = 0;; spins++) {
+                const unsigned f = lane < b ? ld_acquire_u32(flag_g + lane) : epoch;
+                if (__all_sync(0xffffffffu, f == epoch)) break;
+                if (spins > (1u << 22)) {
+                    if (lane == 0) atomicExch(err_flag, 1);
+                    break;
+                }
+                __nanosleep(64);
+            }
+            __syncwarp();
+            double Q[4];
+            mat2_pow(M, span, Q);
+#pragma unroll 1
+            for (int k0 = 0; k0 < b; k0 += 8) {   // eight payloads per L2 round trip
+                double2 z[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) z[u] = __ldcg(reinterpret_cast<const double2 *>(blk_g + (size_t)(k0 + u < b ? k0 + u : 0) * 64));
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (k0 + u < b) {
+                        const double n0 = fma(Q[0], s0, fma(Q[1], s1, z[u].x)), n1 = fma(Q[2], s0, fma(Q[3], s1, z[u].y));
+                        s0 = n0;
+                        s1 = n1;
+                    }
+            }
         }
-        if (PHASE == 0) *reinterpret_cast<double2 *>(blk_g + (size_t)b * 64) = make_double2(s0, s1);   // used when the block is full
+        prefix(s0, s1, true);
     }
-    if (PHASE == 0) return;
     __syncthreads();
     double s0 = start_s[w][lane][0], s1 = start_s[w][lane][1];
     scan_walk<true>(agg_g, inc_g, t0, t1, M[0], M[1], M[2], M[3], s0, s1);

@@ -138,7 +138,7 @@ struct TcParams {
     int *err_flag;
     long long *prof;     // optional per-CTA cycle counters (PB_TC_PROF=1), nullptr otherwise
     long long *trace;    // optional event timeline of CTA 0, tiles kTraceIt0.. (PB_TC_PROF=1): [kTraceTiles][kTraceRoles][32] clock64 values
-    int dbg;             // development switches (PB_TC_DBG): bit0 skip MMA1, bit1 skip MMA2, bit2 skip the conversion, bit4 skip the TMA loads
+    int dbg;             // development switches (PB_TC_DBG): bit0 skip MMA1, bit1 skip MMA2, bit2 skip the conversion, bit4 skip the TMA loads, bit6 no look-back, bit7 no output arithmetic
     int C, n_tiles, n_cg;
     int hist_rows;       // rows of xhist == FIR taps - 1 (<= 256)
     int last_frames;     // input frames the call's last tile really holds (1..160; the rows behind them are zero-filled by TMA)
@@ -1125,6 +1125,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&mbox_free[e]);
                 }
+                if (p.dbg & 128) return;   // development: no output arithmetic, no stores (wrong results)
                 const f32x2 sb01 = pk2(__uint_as_float(zs[0]), __uint_as_float(zs[1])), sb23 = pk2(__uint_as_float(zs[2]), __uint_as_float(zs[3]));
                 const f32x2 sb45 = pk2(__uint_as_float(zs[4]), __uint_as_float(zs[5])), sb67 = pk2(__uint_as_float(zs[6]), __uint_as_float(zs[7]));
                 // (a partial last tile stores only the outputs its frames have triggered)

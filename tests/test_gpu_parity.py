@@ -704,7 +704,7 @@ def test_k3_two_sweeps_with_few_channel_groups(dtype, channels):
         d_in.upload(x.astype(dtype))
         counts = gpu.process_batch_device(d_in.ptr, sizes, d_out.ptr, total)
         gpu.sync()
-        assert counts == sizes and gpu.last_path() == (3, 4 + 4 * rep)   # sweep, scan (two launches), sweep
+        assert counts == sizes and gpu.last_path() == (3, 3 + 3 * rep)   # aggregate sweep, scan, apply sweep
         y = d_out.download((total, channels), dtype)
         pos = 0
         for i, n in enumerate(sizes):

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 from pipe_b200 import abi, design  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-ch, bf, nb = 1024, 4096, 20
+ch, bf, nb = 1024, 4096, int(os.environ.get("K2_NB", "20"))
 chain = abi.Chain(ch, design.config_stages("chain4"), buffer_frames=bf, max_batch=nb)
 x = torch.empty((bf * nb, ch), dtype=torch.float32, device="cuda:0")
 y = torch.empty((bf * nb, ch), dtype=torch.float32, device="cuda:0")
