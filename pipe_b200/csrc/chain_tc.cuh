@@ -369,6 +369,46 @@ static_assert(kColA1 + 16 * kA1Stages == kColMbox && kColMbox + 2 * kTcBlocks + 
 // they are dead until the next tile's MMA1 touches them again (which waits for the output warps to have read the slice)
 __host__ __device__ constexpr uint32_t d2_col(int s) { return kColX + (s < kRsSlices - 1 ? 32 * s : kTcN - 64); }
 
+// What the MMA1 issuer needs for chunk q, worked out at compile time (constant bank, uniform loads): the issuing warp is a single
+// chain of dependent instructions at ~7 cycles each, and deriving the band window, the instruction descriptors and the table
+// offsets of a chunk in that chain cost ~90 instructions per chunk -- the chunk pace (650 cycles) that the accumulator hand-over
+// between consecutive tiles multiplies by twenty.
+struct TcChunk {
+    uint32_t toff;   // descriptor offset (16 B units) of the Toeplitz window of the chunk
+    uint32_t dcol;   // first accumulator column of the window
+    uint32_t idn;    // instruction descriptor over the columns that already hold partial sums (0: none)
+    uint32_t idw;    // ... over the whole window
+    uint32_t ncol;   // first-touch blocks: column offset inside the window (q < 11) ...
+    uint32_t noff;   // ... and their descriptor offset
+    uint32_t has_new;
+    int32_t blk;     // >= 0: the commit of this chunk completes column block `blk` of D1 (blk_full barrier index)
+};
+__host__ __device__ constexpr uint32_t make_idesc_c(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
+__host__ __device__ constexpr TcChunk make_chunk(int q)
+{
+    int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0;
+    const int hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
+    if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
+    const bool has_new = q < kTcBlocks;
+    const int n_old = has_new ? 2 * q : hi - lo + 1;
+    return TcChunk{(uint32_t)((52 - 2 * q + lo) * 128) >> 4,
+                   (uint32_t)(8 * lo),
+                   n_old > 0 ? make_idesc_c(8 * n_old) : 0u,
+                   make_idesc_c(8 * (hi - lo + 1)),
+                   (uint32_t)(8 * n_old),
+                   has_new ? (uint32_t)(n_old * 128) >> 4 : 0u,
+                   has_new ? 1u : 0u,
+                   q >= kTcFirstDone ? q - kTcFirstDone : -1};
+}
+struct TcChunkTab {
+    TcChunk c[kTcChunks];
+    constexpr TcChunkTab() : c{}
+    {
+        for (int q = 0; q < kTcChunks; q++) c[q] = make_chunk(q);
+    }
+};
+static __constant__ TcChunkTab c_tc_chunks = TcChunkTab();
+
 }  // namespace tc
 
 // One block of 16 FIR columns of one channel: f on the channel's grid = (E + X) * fscale -> pieces f0 (integer grid) + f1, packed
@@ -605,46 +645,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             if (PROF == 1) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
             const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
             const int n_chunks = my_tiles * kTcChunks;
-            // the MMAs of chunk g (running number over this CTA's tiles); called by the elected lane only
-            auto issue_chunk = [&](int g) {
-                const int it = g / kTcChunks, q = g - it * kTcChunks;
-                const int s = g % kA1Stages;
+            // the MMAs of chunk q of a tile, A operand in ring stage st; called by the elected lane only
+            auto issue_chunk = [&](int q, int st) {
                 // Window of chunk q in 8-column blocks: [lo, hi], widened to an even count.  For q <= 10 its last two blocks
                 // (2q, 2q+1) are touched for the first time in this tile: they are written with accumulate = 0 by a
                 // separate N = 16 instruction, so D1 never needs zeroing and the previous tile only has to have
                 // released column block q (16 columns) before chunk q -- MMA1 of the next tile overlaps that tile's tail.
-                int lo = 2 * q - 33 > 0 ? 2 * q - 33 : 0, hi = 2 * q + 1 < kTcN / 8 - 1 ? 2 * q + 1 : kTcN / 8 - 1;
-                if ((hi - lo + 1) & 1) lo--;  // odd only when lo > 0
-                const bool has_new = q < kTcBlocks;           // blocks 2q, 2q+1 are new
-                const int n_old = has_new ? 2 * q : hi - lo + 1;  // 8-column blocks that already hold partial sums
-                const uint32_t toff = (uint32_t)((52 - 2 * q + lo) * 128) >> 4;
-                const uint32_t a0 = tmem_base + kColA1 + 16 * s, a1 = a0 + 8;   // x0, x1 pieces of the chunk
-                const uint64_t b0 = bd0 + toff, b1 = bd1 + toff, b2 = bd2 + toff, b3 = bd3 + toff;
-                const uint32_t dE = tmem_base + kColE + 8 * lo, dX = tmem_base + kColX + 8 * lo;
+                const TcChunk k = c_tc_chunks.c[q];
+                const uint32_t a0 = tmem_base + kColA1 + 16 * st, a1 = a0 + 8;   // x0, x1 pieces of the chunk
+                const uint64_t b0 = bd0 + k.toff, b1 = bd1 + k.toff, b2 = bd2 + k.toff, b3 = bd3 + k.toff;
+                const uint32_t dE = tmem_base + kColE + k.dcol, dX = dE + (kColX - kColE);
                 if (!(p.dbg & 1)) {
-                    if (n_old > 0) {
-                        const uint32_t idn = make_idesc(8 * n_old);
-                        umma_ts(dE, a0, b0, idn, 1);   // x0 h0: exact, integers < 2^24
-                        umma_ts(dX, a0, b1, idn, 1);   // x0 (h1 + h2): the tap's remainder in two pieces
+                    if (k.idn) {
+                        umma_ts(dE, a0, b0, k.idn, 1);   // x0 h0: exact, integers < 2^24
+                        umma_ts(dX, a0, b1, k.idn, 1);   // x0 (h1 + h2): the tap's remainder in two pieces
                     }
-                    if (has_new) {
-                        const uint32_t idn = make_idesc(16), off = (uint32_t)(n_old * 128) >> 4;
-                        umma_ts(dE + 8 * n_old, a0, b0 + off, idn, 0);
-                        umma_ts(dX + 8 * n_old, a0, b1 + off, idn, 0);
+                    if (k.has_new) {
+                        constexpr uint32_t id16 = make_idesc_c(16);
+                        umma_ts(dE + k.ncol, a0, b0 + k.noff, id16, 0);
+                        umma_ts(dX + k.ncol, a0, b1 + k.noff, id16, 0);
                     }
-                    const uint32_t idw = make_idesc(8 * (hi - lo + 1));
-                    umma_ts(dX, a0, b2, idw, 1);
-                    umma_ts(dX, a1, b3, idw, 1);       // x1 h: |x1| <= 1/2, the tap rounded once (2^-12 relative) is enough
+                    umma_ts(dX, a0, b2, k.idw, 1);
+                    umma_ts(dX, a1, b3, k.idw, 1);       // x1 h: |x1| <= 1/2, the tap rounded once (2^-12 relative) is enough
                 }
-                umma_commit(&a1_empty[s]);  // frees the A stage when these MMAs have read it
-                if (q >= kTcFirstDone) umma_commit(&blk_full[q - kTcFirstDone]);  // column block q-17 (after 26: 9 and 10) is final
+                umma_commit(&a1_empty[st]);  // frees the A stage when these MMAs have read it
+                if (k.blk >= 0) umma_commit(&blk_full[k.blk]);  // column block q-17 (after 26: 9 and 10) is final
             };
             // The issuing warp is a serial chain of long-latency instructions (mbarrier test ~90 cycles, fence, elect, ~45 per
             // UTCHMMA issue, ~60 per commit): it takes TWO chunks -- the pair one converter group hands over together -- per
             // wait / elect round trip, otherwise the tensor pipe idles behind it (measured: 870 cycles per chunk for ~400 of MMA).
+            int ita = 0, qa = 0;   // tile and chunk of ga, kept incrementally
             for (int ga = 0; ga < n_chunks; ga += 2) {
                 const int gb = ga + 1 < n_chunks ? ga + 1 : ga;
-                const int ita = ga / kTcChunks, qa = ga - ita * kTcChunks, itb = gb / kTcChunks, qb = gb - itb * kTcChunks;
+                const int qb = gb == ga ? qa : (qa + 1 < kTcChunks ? qa + 1 : 0), itb = (gb != ga && qa + 1 == kTcChunks) ? ita + 1 : ita;
                 long long c0 = (PROF == 1 ? clk() : 0ll);
                 // First touch of column block q (q < 11): its E columns hold the previous tile's f pieces until that tile's MMA2
                 // slice has read them, its X columns the resampler sums of slice q/2 (blocks 7..10: slice 4) until the output
@@ -658,14 +691,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 w_c += c1 - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 if (elect_one()) {
-                    issue_chunk(ga);
-                    if (gb != ga) issue_chunk(gb);
+                    issue_chunk(qa, ga % kA1Stages);
+                    if (gb != ga) issue_chunk(qb, gb % kA1Stages);
                 }
                 __syncwarp();
                 const long long c2 = (PROF == 1 ? clk() : 0ll);
                 w_i += c2 - c1;
                 PB_TRACE(0, ita, qa);
                 if (gb != ga) PB_TRACE(0, itb, qb);
+                qa += 2;
+                if (qa >= kTcChunks) { qa -= kTcChunks; ita++; }
             }
             if (PROF == 1 && p.prof && lane == 0) {
                 long long *pr = p.prof + blockIdx.x * kProfCount;
