@@ -76,6 +76,7 @@ struct Segment {
     // K3 (streaming kernels): runs without FIR and without resampler
     bool st_ok = false;
     int st_grid = 0, st_agg_grid = 0;
+    double st_tile_step[4] = {1, 0, 0, 1};          // K3: the biquad state step over one tile (the table entry the kernels call A^T)
     void *d_st_tab = nullptr;                        // StTab
     void *d_scan_blk = nullptr;                      // K3 two sweeps: block aggregates of the scan [groups][kScanBlocks][32][2] doubles
     double st_wt[32][2] = {};                        // A^k B, passed in the kernel parameters
@@ -828,6 +829,7 @@ static int32_t refresh_segment_params(pb_chain *c, Segment &s)
                 for (int e = 0; e < 4; e++) tab[StTab::kMw + 4 * w + e] = W[e];
                 mul(W, A32, W);
             }
+            for (int e = 0; e < 4; e++) s.st_tile_step[e] = AT[e];
             PB_CUDA(upload<double>(s.d_st_tab, tab));
         }
     }
@@ -1097,10 +1099,37 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
         // block aggregates: the first kScanBlocks slots of the (otherwise unused) inclusive-state array of the LAST tile row would
         // alias live data, so they have their own scratch behind the look-back arrays
         const dim3 sgrid((unsigned)p.n_groups, (unsigned)kScanBlocks);
-        const size_t blk_doubles = 64 * (size_t)kScanBlocks * (size_t)p.n_groups;
-        stream_scan_kernel<<<sgrid, kScanWarps * 32, 0, stream>>>(p.lb_agg, p.lb_inc, (double *)s.d_scan_blk,
-                                                                  reinterpret_cast<unsigned *>((double *)s.d_scan_blk + blk_doubles), p.bq_state,
-                                                                  p.tab, c->C, p.n_tiles, p.n_tiles - 1, p.epoch, p.err_flag);
+        ScanParams sp{};
+        sp.agg = p.lb_agg;
+        sp.inc = p.lb_inc;
+        sp.blk = (double *)s.d_scan_blk;
+        sp.flags = reinterpret_cast<unsigned *>(sp.blk + 64 * (size_t)kScanBlocks * (size_t)p.n_groups);
+        sp.bq_state = p.bq_state;
+        sp.tab = p.tab;
+        sp.err_flag = p.err_flag;
+        sp.epoch = p.epoch;
+        sp.C = c->C;
+        sp.n_tiles = p.n_tiles;
+        sp.n_full = p.n_tiles - 1;
+        sp.span = (sp.n_full + kScanBlocks - 1) / kScanBlocks;
+        sp.per = (sp.span + kScanWarps - 1) / kScanWarps;
+        {   // powers of the tile step over a segment and over a block (2x2, double, on the host)
+            auto mpow = [](const double *M, int e, double *P) {
+                double B[4] = {M[0], M[1], M[2], M[3]}, R[4] = {1.0, 0.0, 0.0, 1.0};
+                for (; e > 0; e >>= 1) {
+                    if (e & 1) {
+                        const double r[4] = {R[0] * B[0] + R[1] * B[2], R[0] * B[1] + R[1] * B[3], R[2] * B[0] + R[3] * B[2], R[2] * B[1] + R[3] * B[3]};
+                        for (int i = 0; i < 4; i++) R[i] = r[i];
+                    }
+                    const double q[4] = {B[0] * B[0] + B[1] * B[2], B[0] * B[1] + B[1] * B[3], B[2] * B[0] + B[3] * B[2], B[2] * B[1] + B[3] * B[3]};
+                    for (int i = 0; i < 4; i++) B[i] = q[i];
+                }
+                for (int i = 0; i < 4; i++) P[i] = R[i];
+            };
+            mpow(s.st_tile_step, sp.per, sp.Mper);
+            mpow(s.st_tile_step, sp.span, sp.Mspan);
+        }
+        stream_scan_kernel<<<sgrid, kScanWarps * 32, 0, stream>>>(sp);
         PB_CUDA(cudaGetLastError());
         launch_stream_mode<T, kStApply>(p, grid, c->C, stream);
         PB_CUDA(cudaGetLastError());

@@ -537,9 +537,7 @@ __global__ void __launch_bounds__(kStThreads, 4) stream_aggregate_kernel(const _
 // (one CTA each), a block into 32 segments (one warp each, lane = channel).  First: segment aggregates by Horner, prefix over
 // the block's segments from a zero state, block aggregate to global memory.  Then: the block's start state from the carried
 // state and the aggregates of the blocks in front, the same prefix from it, and every warp walks its segment again and stores
-// the inclusive states.  Payloads (L2) are fetched a batch ahead of the recursion.  (These warps are single dependent chains at
-// ~20 cycles per instruction: the launch takes ~15 us whatever its arithmetic; a scan over per-CTA segments instead of tiles
-// measured the same.)
+// the inclusive states.  Payloads (L2) are fetched a batch ahead of the recursion.
 constexpr int kScanWarps = 32, kScanBatch = 4, kScanBlocks = 16;
 template <bool STORE>
 __device__ __forceinline__ void scan_walk(const double *agg_g, double *inc_g, int t0, int t1, double m0, double m1, double m2, double m3,
@@ -589,75 +587,91 @@ __device__ __forceinline__ void mat2_pow(const double (&M)[4], int e, double (&P
 }
 // blk: [n_groups][kScanBlocks][32 lanes][2] block aggregates (scratch in global memory); flags: [n_groups][kScanBlocks] words, the
 // epoch of the launch that wrote the block aggregate (release / acquire).  ONE launch of n_groups x kScanBlocks CTAs (at most 128
-// with the four channel groups two sweeps serve: always co-resident, so a CTA may wait for the CTAs in front of it): every CTA
+// with the channel groups two sweeps serve: always co-resident, so a CTA may wait for the CTAs in front of it): every CTA
 // publishes its block aggregate as soon as it has it and then waits only for the blocks IN FRONT of it, whose aggregates depend
-// on nothing.
-__global__ void __launch_bounds__(kScanWarps * 32) stream_scan_kernel(const double *__restrict__ agg, double *__restrict__ inc,
-                                                                      double *__restrict__ blk, unsigned *__restrict__ flags,
-                                                                      const double *__restrict__ bq_state, const double *__restrict__ tab,
-                                                                      int C, int n_tiles, int n_full, unsigned epoch, int *err_flag)
+// on nothing.  A warp of this kernel is one dependent chain at ~20 cycles per instruction, so what counts is the number of
+// instructions on the longest chain: the 32 segment maps of a block are combined by a Kogge-Stone scan over the warps (five
+// rounds) instead of a 32-step walk by one warp, and the matrix powers come from the host.
+struct ScanParams {
+    const double *agg;
+    double *inc, *blk;
+    unsigned *flags;
+    const double *bq_state, *tab;
+    int *err_flag;
+    unsigned epoch;
+    int C, n_tiles, n_full, span, per;   // tiles per block / per segment (warp)
+    double Mper[4];                      // (tile step)^per: over a whole segment
+    double Mspan[4];                     // (tile step)^span: over a whole block
+};
+__global__ void __launch_bounds__(kScanWarps * 32) stream_scan_kernel(const __grid_constant__ ScanParams p)
 {
-    __shared__ double seg_s[kScanWarps][kCg][2];
-    __shared__ double start_s[kScanWarps][kCg][2];
+    __shared__ double mat_s[2][kScanWarps][4];
+    __shared__ __align__(16) double vec_s[2][kScanWarps][kCg][2];
+    __shared__ __align__(16) double blk_start_s[kCg][2];
     const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = g * kCg + lane;
-    const double *AT = tab + StTab::kPw + 4 * kStWarps;   // the tile step A^T
+    const double *AT = p.tab + StTab::kPw + 4 * kStWarps;   // the tile step A^T
     const double M[4] = {AT[0], AT[1], AT[2], AT[3]};
-    const int span = (n_full + kScanBlocks - 1) / kScanBlocks;   // tiles per block
-    const int b0 = b * span < n_full ? b * span : n_full, b1 = b0 + span < n_full ? b0 + span : n_full;
-    const int per = (span + kScanWarps - 1) / kScanWarps;        // tiles per segment
-    const int t0 = b0 + w * per < b1 ? b0 + w * per : b1, t1 = t0 + per < b1 ? t0 + per : b1;
-    const double *agg_g = agg + (size_t)g * n_tiles * 64 + lane * 2;
-    double *inc_g = inc + (size_t)g * n_tiles * 64 + lane * 2;
-    double *blk_g = blk + ((size_t)g * kScanBlocks) * 64 + lane * 2;
-    unsigned *flag_g = flags + (size_t)g * kScanBlocks;
-    double a0 = 0.0, a1 = 0.0;
-    scan_walk<false>(agg_g, inc_g, t0, t1, M[0], M[1], M[2], M[3], a0, a1);
-    seg_s[w][lane][0] = a0;
-    seg_s[w][lane][1] = a1;
+    const int b0 = b * p.span < p.n_full ? b * p.span : p.n_full, b1 = b0 + p.span < p.n_full ? b0 + p.span : p.n_full;
+    const int t0 = b0 + w * p.per < b1 ? b0 + w * p.per : b1, t1 = t0 + p.per < b1 ? t0 + p.per : b1;
+    const double *agg_g = p.agg + (size_t)g * p.n_tiles * 64 + lane * 2;
+    double *inc_g = p.inc + (size_t)g * p.n_tiles * 64 + lane * 2;
+    double *blk_g = p.blk + ((size_t)g * kScanBlocks) * 64 + lane * 2;
+    unsigned *flag_g = p.flags + (size_t)g * kScanBlocks;
+    // the segment's affine map from a zero state: v <- (tile step)^n v + (what its n tiles add); n = per except at the block's end
+    double v0 = 0.0, v1 = 0.0;
+    scan_walk<false>(agg_g, inc_g, t0, t1, M[0], M[1], M[2], M[3], v0, v1);
+    double W0 = p.Mper[0], W1 = p.Mper[1], W2 = p.Mper[2], W3 = p.Mper[3];
+    const int n = t1 - t0;
+    if (n != p.per) {   // the block's last segment (shorter) and the empty ones behind it
+        double R[4];
+        mat2_pow(M, n, R);
+        W0 = R[0]; W1 = R[1]; W2 = R[2]; W3 = R[3];
+    }
+    int cur = 0;
+    if (lane == 0) {
+        mat_s[0][w][0] = W0; mat_s[0][w][1] = W1; mat_s[0][w][2] = W2; mat_s[0][w][3] = W3;
+    }
+    *reinterpret_cast<double2 *>(vec_s[0][w][lane]) = make_double2(v0, v1);
     __syncthreads();
-    if (w == 0) {
-        double P[4];
-        mat2_pow(M, per, P);
-        // the prefix over the block's segments: from a zero state (-> block aggregate), then again from the block's start state
-        auto prefix = [&](double s0, double s1, bool keep) {
-            for (int k = 0; k < kScanWarps; k++) {
-                if (keep) {
-                    start_s[k][lane][0] = s0;
-                    start_s[k][lane][1] = s1;
-                }
-                // the step over segment k: A^T to the number of tiles it holds (`per`, fewer in the block's last segment, none behind it)
-                const int left = b1 - (b0 + k * per), nk = left < 0 ? 0 : (left > per ? per : left);
-                if (nk == 0) continue;
-                double R[4] = {P[0], P[1], P[2], P[3]};
-                if (nk != per) mat2_pow(M, nk, R);
-                const double n0 = fma(R[0], s0, fma(R[1], s1, seg_s[k][lane][0])), n1 = fma(R[2], s0, fma(R[3], s1, seg_s[k][lane][1]));
-                s0 = n0;
-                s1 = n1;
-            }
-            return make_double2(s0, s1);
-        };
-        if (b + 1 < kScanBlocks) {   // nobody is behind the last block
-            const double2 z = prefix(0.0, 0.0, false);
-            *reinterpret_cast<double2 *>(blk_g + (size_t)b * 64) = z;
+    // inclusive scan of the maps over the warps: (W, v)_w <- (W, v)_w o (W, v)_(w - d)
+#pragma unroll 1
+    for (int d = 1; d < kScanWarps; d <<= 1) {
+        if (w >= d) {
+            const double *Wp = mat_s[cur][w - d];
+            const double p0 = Wp[0], p1 = Wp[1], p2 = Wp[2], p3 = Wp[3];
+            const double2 vp = *reinterpret_cast<const double2 *>(vec_s[cur][w - d][lane]);
+            v0 = fma(W0, vp.x, fma(W1, vp.y, v0));
+            v1 = fma(W2, vp.x, fma(W3, vp.y, v1));
+            const double r0 = W0 * p0 + W1 * p2, r1 = W0 * p1 + W1 * p3, r2 = W2 * p0 + W3 * p2, r3 = W2 * p1 + W3 * p3;
+            W0 = r0; W1 = r1; W2 = r2; W3 = r3;
+        }
+        cur ^= 1;
+        if (lane == 0) {
+            mat_s[cur][w][0] = W0; mat_s[cur][w][1] = W1; mat_s[cur][w][2] = W2; mat_s[cur][w][3] = W3;
+        }
+        *reinterpret_cast<double2 *>(vec_s[cur][w][lane]) = make_double2(v0, v1);
+        __syncthreads();
+    }
+    if (w == kScanWarps - 1) {
+        if (b + 1 < kScanBlocks) {   // the block from a zero state: published for the blocks behind (nobody is behind the last one)
+            *reinterpret_cast<double2 *>(blk_g + (size_t)b * 64) = make_double2(v0, v1);
             __syncwarp();
-            if (lane == 0) st_release_u32(flag_g + b, epoch);
+            if (lane == 0) st_release_u32(flag_g + b, p.epoch);
         }
         // start state of the block: the carried state through the blocks in front (every block in front of this one is full)
-        double s0 = c < C ? bq_state[2 * c] : 0.0, s1 = c < C ? bq_state[2 * c + 1] : 0.0;
+        double s0 = c < p.C ? p.bq_state[2 * c] : 0.0, s1 = c < p.C ? p.bq_state[2 * c + 1] : 0.0;
         if (b > 0) {
             for (unsigned spins = 0;; spins++) {
-                const unsigned f = lane < b ? ld_acquire_u32(flag_g + lane) : epoch;
-                if (__all_sync(0xffffffffu, f == epoch)) break;
+                const unsigned f = lane < b ? ld_acquire_u32(flag_g + lane) : p.epoch;
+                if (__all_sync(0xffffffffu, f == p.epoch)) break;
                 if (spins > (1u << 22)) {
-                    if (lane == 0) atomicExch(err_flag, 1);
+                    if (lane == 0) atomicExch(p.err_flag, 1);
                     break;
                 }
-                __nanosleep(64);
+                __nanosleep(32);
             }
             __syncwarp();
-            double Q[4];
-            mat2_pow(M, span, Q);
 #pragma unroll 1
             for (int k0 = 0; k0 < b; k0 += 8) {   // eight payloads per L2 round trip
                 double2 z[8];
@@ -666,16 +680,24 @@ __global__ void __launch_bounds__(kScanWarps * 32) stream_scan_kernel(const doub
 #pragma unroll
                 for (int u = 0; u < 8; u++)
                     if (k0 + u < b) {
-                        const double n0 = fma(Q[0], s0, fma(Q[1], s1, z[u].x)), n1 = fma(Q[2], s0, fma(Q[3], s1, z[u].y));
+                        const double n0 = fma(p.Mspan[0], s0, fma(p.Mspan[1], s1, z[u].x)), n1 = fma(p.Mspan[2], s0, fma(p.Mspan[3], s1, z[u].y));
                         s0 = n0;
                         s1 = n1;
                     }
             }
         }
-        prefix(s0, s1, true);
+        *reinterpret_cast<double2 *>(blk_start_s[lane]) = make_double2(s0, s1);
     }
     __syncthreads();
-    double s0 = start_s[w][lane][0], s1 = start_s[w][lane][1];
+    // true state at the start of this warp's segment: the map of the segments in front of it applied to the block's start state
+    const double2 bs = *reinterpret_cast<const double2 *>(blk_start_s[lane]);
+    double s0 = bs.x, s1 = bs.y;
+    if (w > 0) {
+        const double *Wp = mat_s[cur][w - 1];
+        const double2 vp = *reinterpret_cast<const double2 *>(vec_s[cur][w - 1][lane]);
+        s0 = fma(Wp[0], bs.x, fma(Wp[1], bs.y, vp.x));
+        s1 = fma(Wp[2], bs.x, fma(Wp[3], bs.y, vp.y));
+    }
     scan_walk<true>(agg_g, inc_g, t0, t1, M[0], M[1], M[2], M[3], s0, s1);
 }
 

@@ -14,7 +14,8 @@ import _oracle as orc  # noqa: E402
 from pipe_b200 import abi, design  # noqa: E402
 
 st = design.config_stages("gain_biquad")
-for ch, bf, dtype in ((64, 3000, np.float32), (33, 1500, np.float32), (40, 700, np.float64)):
+# (64 ch x 70000 frames in one buffer: 274 tiles in 2 channel groups -> the two-sweep path: aggregate sweep, scan, apply sweep)
+for ch, bf, dtype in ((64, 3000, np.float32), (33, 1500, np.float32), (40, 700, np.float64), (64, 70000, np.float32)):
     gpu, cpu = abi.Chain(ch, st, buffer_frames=bf, dtype=dtype, flags=abi.CHAIN_METER), orc.Chain(ch, st)
     for b in range(2):
         x = orc.source_fill(b * bf * ch, bf * ch).reshape(bf, ch)
