@@ -682,6 +682,13 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const Segment::TcPhase
         p.AL_first[i] = s.tc_ALf[i];
         p.A16[i] = s.tc_A16[i];
     }
+    {   // two block steps (balanced coordinates, like A16)
+        const double *a = s.tc_A16;
+        p.A32[0] = a[0] * a[0] + a[1] * a[2];
+        p.A32[1] = a[0] * a[1] + a[1] * a[3];
+        p.A32[2] = a[2] * a[0] + a[3] * a[2];
+        p.A32[3] = a[2] * a[1] + a[3] * a[3];
+    }
     for (int i = 0; i < 16; i++) {  // applied to the raw accumulator sum: fold fscale in
         p.Wz[i][0] = (float)((double)s.tc_Wz[i][0] * (double)p.fscale);
         p.Wz[i][1] = (float)((double)s.tc_Wz[i][1] * (double)p.fscale);

@@ -150,6 +150,7 @@ struct TcParams {
     float descale_rs;    // g_bq * g_out / 2^sh2 (times 1 / sigma_c per channel)
     double b0, b1, b2, a1, a2, g_bq;
     double A16[4];       // block step
+    double A32[4];       // two block steps: the drain groups each chain the blocks of one parity (the early tile aggregate)
     double AL[4];        // A^160: look-back step, incoming state -> state after row 159
     double AL_first[4];  // A^145: the same for tile 0, whose state enters at row 15
     float Wz[16][2];     // zero-state end state of a block on the channel's grid: Z = sum_i Wz[i] * (E+X)_i, Wz[i] = A^(15-i) B * fscale
@@ -354,9 +355,10 @@ constexpr int kOffPark = kOffZx + kZxFloats * 4;                // [128][128] fl
 constexpr int kParkRows = (kRsSlices - 1) * kRsN;               // (the last slice waits in registers: nothing queues behind it)
 constexpr int kOffBar = kOffPark + kParkRows * kTcCh * 4;
 constexpr int kNumBlkBars = kTcChunks - kTcFirstDone;           // 10: one per chunk 17..26
-constexpr int kNumBars = 2 * kRawStages + 2 * kA1Stages + kNumBlkBars + kTcBlocks + kRsSlices + 2 + 1 + 4 + 4 + 4 + 4;
+constexpr int kNumBars = 2 * kRawStages + 2 * kA1Stages + kNumBlkBars + kTcBlocks + kRsSlices + 2 + 1 + 4 + 4 + 4 + 4 + 4;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmemSlot + 16;
+constexpr int kOffSa = ((kOffTmemSlot + 16 + 15) / 16) * 16;                      // [2][128][2] double: drain group A's chained state of the even blocks (per tile parity)
+constexpr int kSmemBytes = kOffSa + 2 * kTcCh * 2 * 8;
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
 static_assert(kOffTab % 128 == 0 && kOffBar % 8 == 0, "alignment");
 
@@ -515,7 +517,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     uint64_t *zx_ready = mbox_free + 4;             // [4]  drain warp B -> drain warp A: the Z of the odd blocks are in shared memory
     uint64_t *szs_ready = zx_ready + 4;             // [4]  drain warp A -> drain warp B: zero-state block states and s10 are in the mailbox
     uint64_t *zx_free = szs_ready + 4;              // [4]  drain warp A -> drain warp B: the previous tile's Z have been read
+    uint64_t *sa_ready = zx_free + 4;               // [4]  drain warp A -> drain warp B: the chained state of the even blocks 0..8 is in shared memory
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmemSlot);
+    double *sa_s = reinterpret_cast<double *>(smem + kOffSa);
 
     // Role numbers (`warp` below) are not the hardware warp ids: a scheduler prefers its highest warp id, so the ids follow
     // the pipeline's priorities -- the three single-warp roles whose latency every tile waits for (TMA producer, the two MMA
@@ -585,6 +589,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&zx_ready[i], 1);
             mbar_init(&szs_ready[i], 1);
             mbar_init(&zx_free[i], 1);
+            mbar_init(&sa_ready[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -863,6 +868,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const bool gl = (warp & 3) == 2;  // first warp of the role group (warps 10 / 14)
             const int gid = roleB ? 4 : 3;
             float *zxt = zx;
+            // Each group chains the zero-state end states of ITS blocks on the way (two block steps per link): the state after row
+            // 159 from a zero state -- the tile's aggregate, which the look-back of the tiles behind waits for -- is then
+            // A^16 (even blocks 0..8) + (odd blocks 1..9), known the moment block 9 has been drained instead of a full 11-step
+            // recursion (~2.5 k cycles) later.
+            double ps1 = 0.0, ps2 = 0.0;
             if (roleB && it > 0) mbar_wait(&zx_free[e], par ^ 1);  // role A has read the previous tile's block sums
 #pragma unroll 1
             for (int b = roleB ? 1 : 0; b < kTcBlocks; b += 2) {
@@ -888,6 +898,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 if (gl && lane == 0) mbar_arrive(&a2_ready[b]);
                 zxt[(2 * b + 0) * kTcCh + e * 32 + lane] = p0;
                 zxt[(2 * b + 1) * kTcCh + e * 32 + lane] = p1;
+                if (b < kTcBlocks - 1) {   // blocks 0..9 make the state after row 159
+                    const double n1 = fma(p.A32[0], ps1, fma(p.A32[1], ps2, f2d_bits(p0)));
+                    const double n2 = fma(p.A32[2], ps1, fma(p.A32[3], ps2, f2d_bits(p1)));
+                    ps1 = n1;
+                    ps2 = n2;
+                }
+                if (!roleB && b == kTcBlocks - 3) {   // after block 8: hand the even chain to group B
+                    *reinterpret_cast<double2 *>(sa_s + ((size_t)(it & 1) * kTcCh + e * 32 + lane) * 2) = make_double2(ps1, ps2);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sa_ready[e]);
+                }
                 if (gl) PB_TRACE(roleB ? 4 : 3, it, b);
                 e_m += (PROF == 1 ? clk() : 0ll) - k1;
             }
@@ -900,10 +921,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             if (!roleB) {
                 // ---- role A: s(b+1) = A^16 s(b) + Z_b in double, on the channel's grid
                 mbar_wait(&zx_ready[e], par);
-                double s10_1 = 0.0, s10_2 = 0.0;  // zero-state state after row 159 (true units)
                 float szs[kTcBlocks][2];          // zero-state state at the start of each block (true units)
                 {
-                    const double isig_d = f2d_bits(isig);
                     double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                     for (int b = 0; b < kTcBlocks; b++) {
@@ -917,28 +936,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                         const double n2 = fma(p.A16[2], s1, fma(p.A16[3], s2, f2d_bits(zxt[(2 * b + 1) * kTcCh + e * 32 + lane])));
                         s1 = n1;
                         s2 = n2;
-                        if (b == kTcBlocks - 2) {  // back to the TDF-II basis and to true units, which the look-back arrays and K1 use
-                            s10_1 = fma(p.Wbi[0], s1, p.Wbi[1] * s2) * isig_d;
-                            s10_2 = fma(p.Wbi[2], s1, p.Wbi[3] * s2) * isig_d;
-                        }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&zx_free[e]);
-                if (chained) {
-                    p.lb_agg[slot * 64 + lane * 2] = s10_1;
-                    p.lb_agg[slot * 64 + lane * 2 + 1] = s10_2;
-                    __syncwarp();
-                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
-                }
                 if (it > 0) mbar_wait(&mbox_free[e], par ^ 1);  // the output warps have read the previous tile's block states
                 asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
                 for (int b = 0; b < kTcBlocks; b++)
                     tmem_st2(tmem_base + lane_base + kColMbox + 2 * b, __float_as_uint(szs[b][0]), __float_as_uint(szs[b][1]));
                 tmem_st2(tmem_base + lane_base + kColMbox + 2 * kTcBlocks, 0u, 0u);  // the last slice reads a fourth, absent block
-                tmem_st2(tmem_base + lane_base + kColS10, (uint32_t)__double2loint(s10_1), (uint32_t)__double2hiint(s10_1));
-                tmem_st2(tmem_base + lane_base + kColS10 + 2, (uint32_t)__double2loint(s10_2), (uint32_t)__double2hiint(s10_2));
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
@@ -950,6 +957,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             // ---- role B
             __syncwarp();
             if (lane == 0) mbar_arrive(&zx_ready[e]);
+            // the tile's aggregate: state after row 159 from a zero state = A^16 (even chain, group A) + (odd chain), back in the
+            // TDF-II basis and in true units, which the look-back arrays and K1 use
+            double s10_1, s10_2;
+            {
+                mbar_wait(&sa_ready[e], par);
+                const double2 sa = *reinterpret_cast<const double2 *>(sa_s + ((size_t)(it & 1) * kTcCh + e * 32 + lane) * 2);
+                const double t1 = fma(p.A16[0], sa.x, fma(p.A16[1], sa.y, ps1)), t2 = fma(p.A16[2], sa.x, fma(p.A16[3], sa.y, ps2));
+                const double isig_d = f2d_bits(isig);
+                s10_1 = fma(p.Wbi[0], t1, p.Wbi[1] * t2) * isig_d;
+                s10_2 = fma(p.Wbi[2], t1, p.Wbi[3] * t2) * isig_d;
+                if (chained) {
+                    p.lb_agg[slot * 64 + lane * 2] = s10_1;
+                    p.lb_agg[slot * 64 + lane * 2 + 1] = s10_2;
+                    __syncwarp();
+                    if (lane == 0) st_release_u32(p.lb_status + slot, (p.epoch << 2) | kLbAgg);
+                }
+            }
             // incoming state: decoupled look-back (same protocol and arrays as K1, 32-channel groups)
             double q1 = 0.0, q2 = 0.0;
             if (first) {
@@ -1007,21 +1031,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             }
             if (gl) PB_TRACE(4, it, 12);   // look-back done
             // ---- true state at the start of every block = zero-state part (role A, in the mailbox) + response to the incoming state
-            double s10_1, s10_2;
             const int end_blk = (PARTIAL && last && p.last_frames < kTcFrames) ? p.last_frames >> 4 : -1;   // block of tile row `last_frames`
             {
                 const float qf0 = d2f_bits(fma(p.Wb[0], q1, p.Wb[1] * q2)), qf1 = d2f_bits(fma(p.Wb[2], q1, p.Wb[3] * q2));
                 const int fi = first ? 1 : 0;
                 mbar_wait(&szs_ready[e], par);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                uint32_t u0[8], u1[8], u2[8], u3[4];
+                uint32_t u0[8], u1[8], u2[8];
                 tmem_ld8(tmem_base + lane_base + kColMbox, u0);
                 tmem_ld8(tmem_base + lane_base + kColMbox + 8, u1);
                 tmem_ld8(tmem_base + lane_base + kColMbox + 16, u2);   // blocks 8..10, the zero pad
-                tmem_ld4(tmem_base + lane_base + kColS10, u3);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                s10_1 = __hiloint2double((int)u3[1], (int)u3[0]);
-                s10_2 = __hiloint2double((int)u3[3], (int)u3[2]);
 #pragma unroll
                 for (int b = 0; b < kTcBlocks; b++) {
                     const float *M = p.Mb[fi][b];
