@@ -592,6 +592,8 @@ static int32_t tc_configure_once(int device)
             err[device] = cudaFuncSetAttribute(chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
         if (err[device] == cudaSuccess)
             err[device] = cudaFuncSetAttribute(chain_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+        if (err[device] == cudaSuccess)
+            err[device] = cudaFuncSetAttribute(chain_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     });
     PB_CUDA(err[device]);
     return PB_OK;
@@ -725,6 +727,7 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const Segment::TcPhase
         p.meter_sumsq = mtr ? mtr + c->C : nullptr;
         if (prof_mode == 1) chain_tc_kernel<1><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
         else if (prof_mode == 2) chain_tc_kernel<2><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
+        else if (p.dbg != 0) chain_tc_kernel<0, false, true><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);   // development switches (whole tiles only)
         else if (p.last_frames < kTcFrames) chain_tc_kernel<0, true><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
         else chain_tc_kernel<0><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
         PB_CUDA(cudaGetLastError());

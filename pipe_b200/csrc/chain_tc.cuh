@@ -495,9 +495,12 @@ __device__ __noinline__ void tc_partial_tail(uint32_t taddr_a, uint32_t taddr_b,
 // per tile), 2 = event timeline of CTA 0 only (PB_TC_PROF=2; nearly free)
 // PARTIAL: the call's last tile may hold fewer than 160 frames (a separate instantiation: the few extra instructions in the output
 // and drain warps cost a whole-tile batch 6 %, measured -- this kernel is that sensitive to its register allocation).
-template <int PROF, bool PARTIAL = false>
+// DBG: the development switches of TcParams::dbg are compiled in (a separate instantiation, launched only when PB_TC_DBG is set: tested
+// at run time they cost the converter ~15 instructions per chunk).
+template <int PROF, bool PARTIAL = false, bool DBG = false>
 __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_constant__ TcParams p)
 {
+    const int dbg = DBG ? p.dbg : 0;
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *raw = smem + kOffRaw;
@@ -619,7 +622,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     const long long c0 = (PROF == 1 ? clk() : 0ll);
                     mbar_wait(&raw_empty[s], ph ^ 1);
                     pw += (PROF == 1 ? clk() : 0ll) - c0;
-                    if (p.dbg & 16) {  // development: no loads
+                    if (dbg & 16) {  // development: no loads
                         mbar_arrive(&raw_full[s]);
                         if (++s == kRawStages) { s = 0; ph ^= 1; }
                         continue;
@@ -660,7 +663,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 const uint32_t a0 = tmem_base + kColA1 + 16 * st, a1 = a0 + 8;   // x0, x1 pieces of the chunk
                 const uint64_t b0 = bd0 + k.toff, b1 = bd1 + k.toff, b2 = bd2 + k.toff, b3 = bd3 + k.toff;
                 const uint32_t dE = tmem_base + kColE + k.dcol, dX = dE + (kColX - kColE);
-                if (!(p.dbg & 1)) {
+                if (!(dbg & 1)) {
                     if (k.idn) {
                         umma_ts(dE, a0, b0, k.idn, 1);   // x0 h0: exact, integers < 2^24
                         umma_ts(dX, a0, b1, k.idn, 1);   // x0 (h1 + h2): the tap's remainder in two pieces
@@ -754,7 +757,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const float *src = reinterpret_cast<const float *>(raw + st * kRawStageBytes) + e * 32 + lane;
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = (p.dbg & 4) ? 0.f : src[i * kTcCh];
+            for (int i = 0; i < 16; i++) v[i] = (dbg & 4) ? 0.f : src[i * kTcCh];
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -781,7 +784,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&raw_empty[st]);
             }
-            if (!(p.dbg & 32)) tmem_st16(tmem_base + lane_base + kColA1 + 16 * st, hi, lo);   // x0: 8 columns, x1: 8 columns
+            if (!(dbg & 32)) tmem_st16(tmem_base + lane_base + kColA1 + 16 * st, hi, lo);   // x0: 8 columns, x1: 8 columns
             if (last) {
                 // carried FIR input history: frames [n-hist_rows, n) in gain-scaled units (K1's convention)
                 // (the window ends kTcFrames - last_frames rows behind the call's last frame when the last tile is partial)
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             if (first) {
                 q1 = p.bq_state[2 * c];
                 q2 = p.bq_state[2 * c + 1];
-            } else if (p.dbg & 64) {   // development: no look-back (wrong results)
+            } else if (dbg & 64) {   // development: no look-back (wrong results)
             } else {
                 const int base = t - 1, j = base - lane;
                 int first_inc = 0;
@@ -1180,7 +1183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&mbox_free[e]);
                 }
-                if (p.dbg & 128) return;   // development: no output arithmetic, no stores (wrong results)
+                if (dbg & 128) return;   // development: no output arithmetic, no stores (wrong results)
                 const f32x2 sb01 = pk2(__uint_as_float(zs[0]), __uint_as_float(zs[1])), sb23 = pk2(__uint_as_float(zs[2]), __uint_as_float(zs[3]));
                 const f32x2 sb45 = pk2(__uint_as_float(zs[4]), __uint_as_float(zs[5])), sb67 = pk2(__uint_as_float(zs[6]), __uint_as_float(zs[7]));
                 // (a partial last tile stores only the outputs its frames have triggered)
@@ -1258,7 +1261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                         const uint32_t f0 = tmem_base + kColE + 16 * (2 * s + k), f1 = f0 + 8;   // the pieces of block 2s+k
                         const uint32_t tb = b2 + ((first && pair == 0) ? kRsPairs : pair) * 2048;
                         const uint64_t r0 = make_desc(tb, 128, 256), r1 = make_desc(tb + 1024, 128, 256);
-                        if (!(p.dbg & 2) && elect_one()) {
+                        if (!(dbg & 2) && elect_one()) {
                             umma_ts(dE, f0, r0, idesc64, k > 0);  // f0 * [p0 | p1] -> [E2 | X2]; E2 exact: integers < 2^24
                             umma_ts(dX, f1, r0, idesc32, 1);
                             umma_ts(dX, f1, r1, idesc32, 1);
