@@ -575,7 +575,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     if (tid == 32) {
         for (int i = 0; i < kRawStages; i++) {
             mbar_init(&raw_full[i], 1);
-            mbar_init(&raw_empty[i], 4);   // every warp of the converter group releases the stage as soon as it has read it
+            mbar_init(&raw_empty[i], 1);   // the converter group's leader releases the stage once the group has read it (one arrival
+                                           // instead of four: every mbarrier arrival of the CTA wakes every parked warp)
         }
         for (int i = 0; i < kA1Stages; i++) {
             mbar_init(&a1_full[i], 1);
@@ -780,10 +781,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                 for (int i = 0; i < 16; i += 2) m = fmaxf(m, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
                 amax = fmaxf(amax, m * fabsf(gsc));
             }
-            if (!last) {   // the values are in registers: hand the stage back to the TMA producer (the last tile still reads v[] below)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_empty[st]);
-            }
             if (!(dbg & 32)) tmem_st16(tmem_base + lane_base + kColA1 + 16 * st, hi, lo);   // x0: 8 columns, x1: 8 columns
             if (last) {
                 // carried FIR input history: frames [n-hist_rows, n) in gain-scaled units (K1's convention)
@@ -794,8 +791,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
                     for (int i = 0; i < 16; i++)
                         if (hrow0 + i >= 0 && hrow0 + i < p.hist_rows) p.xhist_next[(size_t)(hrow0 + i) * p.C + c] = v[i] * gsc;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_empty[st]);
             }
         };
         static_assert(kRawStages == 8 && kA1Stages == 8, "the converter uses one stage index (g & 7) for both rings");
@@ -832,6 +827,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             if (gl && lane == 0) {
                 mbar_arrive(&a1_full[sa]);
                 if (two) mbar_arrive(&a1_full[sb]);
+                mbar_arrive(&raw_empty[sa]);   // (the group has read both chunks out of shared memory: the barrier above)
+                if (two) mbar_arrive(&raw_empty[sb]);
             }
             if (gl) PB_TRACE(1 + grp, ita, qa);
             w_w += (PROF == 1 ? clk() : 0ll) - c2;
