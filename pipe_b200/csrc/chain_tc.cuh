@@ -64,8 +64,9 @@
 // Roles (864 threads, one persistent CTA per SM): warp 0 TMA producer (8-stage ring of 8 KB chunks, one box of
 // 128 channels x 16 frames each), warp 1 MMA1 issuer, warps 2-5 / 6-9 two converter groups on alternate chunks (one warp
 // per TMEM lane quadrant), warps 10-13 / 14-17 two FIR drain groups on the even / odd 16-column blocks of D1 (D1 -> f
-// pieces, block by block as MMA1's last chunks complete them; the first group then runs the block-state recursion and
-// the look-back), warps 18-21 / 22-25 two output groups on the two halves of every slice (D2 -> registers, free the
+// pieces, block by block as MMA1's last chunks complete them, each group chaining the zero-state end states of its blocks on
+// the way; once block 9 is drained the second group combines the two chains into the tile's aggregate, publishes it and does
+// the look-back while the first group runs the block-state recursion), warps 18-21 / 22-25 two output groups on the two halves of every slice (D2 -> registers, free the
 // buffer, block-state correction, coalesced stores, meter), warp 26 MMA2 issuer.  Tiles follow a static time-major
 // schedule: the look-back spins on tiles owned by other CTAs of the same grid, so the grid (<= one CTA per SM) must be
 // co-resident -- true whenever the device is not shared with another long-running kernel.  The drain warps hand the 11
