@@ -59,8 +59,8 @@ struct Segment {
     bool tc_level_ok = true;                         // the biquad keeps the broadband level (see build_tc_tables)
     double tc_fir_l1 = 0;                            // sum |h|: bounds the FIR output on the channel's grid (fp16 range of the f pieces)
     // per-channel block exponent of K2 (chain_tc.cuh): two ping-pong copies of {sigma[C], 1/sigma[C]} and of the measured peaks
-    float *d_tc_scale = nullptr;                     // [2][2][C]
-    unsigned *d_tc_peak = nullptr;                   // [2][C]
+    float *d_tc_scale = nullptr;                     // [2 copies][sigma, 1 / sigma][2 scale classes][C]
+    unsigned *d_tc_peak = nullptr;                   // [2 copies][2 scale classes][C]
     int tc_k = 0;                                    // copy the next call's pass A reads
     std::vector<float> tc_rc;                        // [147 + 32][8] output correction per block state (see chain_tc.cuh)
     // K2 tiles start at the first frame of a call, whatever the resampler's integer phase is there (160 input frames give 147
@@ -602,14 +602,16 @@ static int32_t tc_configure_once(int device)
 static int32_t tc_reset_scales(pb_chain *c, Segment &s, cudaStream_t stream)
 {
     // before the first call nothing is known about the levels: assume full scale (|g x| = 1); pass B corrects it
-    std::vector<float> init((size_t)4 * c->C);
+    // layout: [2 ping-pong copies][sigma | 1 / sigma][2 scale classes][C]
+    const size_t C2 = 2 * (size_t)c->C;
+    std::vector<float> init(4 * C2);
     for (int k = 0; k < 2; k++)
-        for (int i = 0; i < c->C; i++) {
-            init[(size_t)(2 * k) * c->C + i] = kSigTarget;
-            init[(size_t)(2 * k + 1) * c->C + i] = 1.0f / kSigTarget;
+        for (size_t i = 0; i < C2; i++) {
+            init[(size_t)(2 * k) * C2 + i] = kSigTarget;
+            init[(size_t)(2 * k + 1) * C2 + i] = 1.0f / kSigTarget;
         }
     PB_CUDA(cudaMemcpyAsync(s.d_tc_scale, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-    PB_CUDA(cudaMemsetAsync(s.d_tc_peak, 0, sizeof(unsigned) * 2 * (size_t)c->C, stream));
+    PB_CUDA(cudaMemsetAsync(s.d_tc_peak, 0, sizeof(unsigned) * 2 * C2, stream));
     PB_CUDA(cudaStreamSynchronize(stream));  // `init` is pageable host memory
     s.tc_k = 0;
     return PB_OK;
@@ -660,10 +662,10 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const Segment::TcPhase
     const bool meter = is_last_segment && (c->flags & PB_CHAIN_METER);
     p.meter_main = meter ? c->d_meter : nullptr;
     p.meter_scratch = meter ? c->d_meter_scratch : nullptr;
-    p.scale = s.d_tc_scale + (size_t)s.tc_k * 2 * c->C;
-    p.scale_next = s.d_tc_scale + (size_t)(s.tc_k ^ 1) * 2 * c->C;
-    p.peak = s.d_tc_peak + (size_t)s.tc_k * c->C;
-    p.peak_next = s.d_tc_peak + (size_t)(s.tc_k ^ 1) * c->C;
+    p.scale = s.d_tc_scale + (size_t)s.tc_k * 4 * c->C;
+    p.scale_next = s.d_tc_scale + (size_t)(s.tc_k ^ 1) * 4 * c->C;
+    p.peak = s.d_tc_peak + (size_t)s.tc_k * 2 * c->C;
+    p.peak_next = s.d_tc_peak + (size_t)(s.tc_k ^ 1) * 2 * c->C;
     p.err_flag = reinterpret_cast<int *>(c->d_ticket + 1);
     p.C = c->C;
     // the last tile may be partial: TMA zero-fills the rows behind the call's last frame, the kernel stores only the outputs the
@@ -956,8 +958,8 @@ static int32_t build_segment(pb_chain *c, Segment &s)
     if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_tables, (size_t)TcTables::kBytes));
     if (s.tc_ok) PB_CUDA(cudaMalloc(&s.d_tc_rc, (size_t)kTcRcRows * 8 * sizeof(float)));
     if (s.tc_ok) {
-        PB_CUDA(cudaMalloc((void **)&s.d_tc_scale, sizeof(float) * 4 * (size_t)c->C));
-        PB_CUDA(cudaMalloc((void **)&s.d_tc_peak, sizeof(unsigned) * 2 * (size_t)c->C));
+        PB_CUDA(cudaMalloc((void **)&s.d_tc_scale, sizeof(float) * 8 * (size_t)c->C));   // [2 copies][sigma, 1 / sigma][2 classes][C]
+        PB_CUDA(cudaMalloc((void **)&s.d_tc_peak, sizeof(unsigned) * 4 * (size_t)c->C));  // [2 copies][2 classes][C]
         int32_t r = tc_reset_scales(c, s, c->st_compute);
         if (r != PB_OK) return r;
     }

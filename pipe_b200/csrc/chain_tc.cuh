@@ -105,6 +105,12 @@ constexpr int kRsSlices = 5;        // slices of 32 outputs; slice s reads row b
 constexpr int kRsN = 32;
 constexpr int kRsPairs = 19;        // (slice, block) blocks of P; entry 19 is (0, 0) for tile 0 (rows 0..14 are y history)
 
+// Two scale classes per channel: tiles 0 and 1 of a call, whose windows reach into the carried history (class 0), and all the others
+// (class 1).  With one scale per call a channel that was loud in the previous call and is quiet in this one would be served on the
+// loud grid to the end of the call, and the carried state it leaves behind (biquad state, y history) would carry the loud grid's
+// absolute error into the next call (found by tools/k2_soak.py: 1e-4 of the quiet channel's peak in the first outputs of that call).
+constexpr int kTcHistTiles = 2;
+__host__ __device__ constexpr int tc_scale_class(int t) { return t < kTcHistTiles ? 0 : 1; }
 // per-channel scale window, in grid units of the channel's peak |g x| (the x0 piece must stay below 2048)
 constexpr float kSigTarget = 1900.f, kSigLo = 1400.f, kSigHi = 2047.f, kSigCap = 7.9e28f /* 2^96 */;
 
@@ -130,11 +136,11 @@ struct TcParams {
     unsigned *lb_status;
     double *meter_peak, *meter_sumsq;       // where THIS pass accumulates (pass A: the scratch copy, pass B: the chain's meter); or nullptr
     double *meter_main, *meter_scratch;     // [2][C] each: pass B's prologue folds (or drops) what pass A accumulated
-    // per-channel block exponent (see the header comment): scale[0] = sigma, scale[1] = 1 / sigma, [C] each
+    // per-channel block exponent (see the header comment): scale[0] = sigma, scale[1] = 1 / sigma, [2 classes][C] each (tc_scale_class)
     const float *scale;       // used by pass A
     float *scale_next;        // written by pass B's prologue from the peaks pass A measured; used by pass B and by the next call
-    unsigned *peak;           // [C] float bits of max |g x| over the call's windows (pass A: atomicMax)
-    unsigned *peak_next;      // [C] zeroed by pass B's prologue for the next call
+    unsigned *peak;           // [2 classes][C] float bits of max |g x| over the windows of the class's tiles (pass A: atomicMax)
+    unsigned *peak_next;      // [2 classes][C] zeroed by pass B's prologue for the next call
     int pass;                 // 0: pass A (speculated scales, measures the peaks); 1: pass B (verifies; redoes the call if needed)
     int *err_flag;
     long long *prof;     // optional per-CTA cycle counters (PB_TC_PROF=1), nullptr otherwise
@@ -542,13 +548,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     const float *scale = p.scale;
     if (p.pass == 1) {
         int bad = 0;
-        for (int c = tid; c < p.C; c += kTcThreads) {
+        for (int c = tid; c < 2 * p.C; c += kTcThreads) {   // both scale classes of every channel
             const float pk = __uint_as_float(p.peak[c]), su = p.scale[c];
             const float units = pk * su;
             bad |= (units > kSigHi) || (pk > 0.f && units < kSigLo);
             const float ns = pk > 0.f ? fminf(kSigTarget / pk, kSigCap) : su;
             p.scale_next[c] = ns;
-            p.scale_next[p.C + c] = 1.0f / ns;
+            p.scale_next[2 * p.C + c] = 1.0f / ns;
             p.peak_next[c] = 0u;
         }
         const int rerun = __syncthreads_or(bad);
@@ -566,7 +572,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         if (!rerun) return;
         scale = p.scale_next;
     }
-    const float *iscale = scale + p.C;
+    const float *iscale = scale + 2 * p.C;
 
     // ---- one-time setup ------------------------------------------------------------
     if (warp == 0) {
@@ -736,21 +742,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         long long w_r = 0, w_c = 0, w_w = 0;
         const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int n_chunks = my_tiles * kTcChunks;
-        int cur_it = -1, c = 0, f0 = 0;
-        bool last = false;
+        int cur_it = -1, c = 0, f0 = 0, sc_idx = 0;
+        bool last = false, early = false;
         float sig = 0.f, amax = 0.f;
         // one chunk (tile `it` of this CTA, chunk q of the tile, ring stage st): shared memory -> registers -> pieces -> tensor
         // memory (no synchronisation in here)
         auto convert = [&](int it, int q, int st) {
             if (it != cur_it) {   // once per tile
-                if (track && cur_it >= 0) atomicMax(p.peak + c, __float_as_uint(amax));
+                if (track && cur_it >= 0) atomicMax(p.peak + sc_idx, __float_as_uint(amax));
                 cur_it = it;
                 const int tile = blockIdx.x + it * gridDim.x;
                 const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
                 f0 = t * kTcFrames;
                 last = (t == p.n_tiles - 1);
                 c = cg * kTcCh + e * 32 + lane;
-                sig = scale[c];
+                sc_idx = tc_scale_class(t) * p.C + c;
+                // the first two tiles of class 1 look back at frames that are "new" in tiles of class 0: they measure their whole window
+                early = (t >= kTcHistTiles && t < 2 * kTcHistTiles);
+                sig = scale[sc_idx];
                 amax = 0.f;
             }
             const bool hist = (f0 - kTcLead + 16 * q) < 0;
@@ -776,7 +785,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             }
             // peak of |g x| (true units) for the scale check: every frame of the call is "new" (chunks 17..26) in exactly one tile;
             // the history frames are seen by the first tiles only
-            if (track && (q >= kTcFirstDone || hist)) {
+            if (track && (q >= kTcFirstDone || hist || early)) {
                 float m = 0.f;
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) m = fmaxf(m, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
@@ -836,7 +845,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             qa += 4;
             if (qa >= kTcChunks) { qa -= kTcChunks; ita++; }
         }
-        if (track && cur_it >= 0) atomicMax(p.peak + c, __float_as_uint(amax));
+        if (track && cur_it >= 0) atomicMax(p.peak + sc_idx, __float_as_uint(amax));
         if (PROF == 1 && p.prof && warp == 2 && lane == 0) {
             long long *pr = p.prof + blockIdx.x * kProfCount;
             pr[kProfCvtWaitRaw] = w_r;
@@ -865,7 +874,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const size_t slot = (size_t)grp * p.n_tiles + t;
             const bool chained = !first && !last;
             const float *yh = p.yhist + c;
-            const float sig = scale[c], isig = iscale[c];
+            const float sig = scale[tc_scale_class(t) * p.C + c], isig = iscale[tc_scale_class(t) * p.C + c];
             const bool gl = (warp & 3) == 2;  // first warp of the role group (warps 10 / 14)
             const int gid = roleB ? 4 : 3;
             float *zxt = zx;
@@ -1128,7 +1137,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const int c = cg * kTcCh + e * 32 + lane;
             const uint32_t par = it & 1;
             float *outp = p.out + (size_t)t * kTcOut * p.C + c;
-            const float dsc = p.descale_rs * iscale[c];
+            const float dsc = p.descale_rs * iscale[tc_scale_class(t) * p.C + c];
             float m_peak = 0.f;
             double m_sumsq = 0.0;
             const bool meter = p.meter_peak != nullptr;

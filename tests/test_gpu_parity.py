@@ -472,9 +472,10 @@ def test_k2_serves_input_beyond_full_scale():
 def test_k2_level_jumps_between_calls_are_redone_with_the_exact_scale():
     # the scale of a call is speculated from the previous call's peak and verified: a channel that gets 30 dB louder or quieter
     # from one buffer to the next leaves the grid window, and the call is redone (pass B) -- results, carried state and the
-    # fused meter must come out as if nothing had happened.  Contract: the error of a call is bounded by
-    # 1e-6 of the channel's peak over the call AND the state it inherited, so the buffer right after a 30 dB drop is held to
-    # the previous buffer's peak (its carried biquad state and y history were computed on the louder grid).
+    # fused meter must come out as if nothing had happened.  Contract: the first two tiles of a call, whose
+    # windows reach into the carried history, have their own scale: the START of the buffer right after a 30 dB drop is held to the
+    # previous buffer's peak (it inherits state computed on the louder grid), but behind those tiles the buffer is served on its own
+    # grid, and the buffer after it is within 1e-6 of its own peak from its first frame (tools/k2_soak.py found that it was not).
     ch, bf = 128, 1600
     st = design.config_stages("chain4")
     gpu, cpu = abi.Chain(ch, st, buffer_frames=bf, flags=abi.CHAIN_METER), orc.Chain(ch, st)
@@ -492,14 +493,47 @@ def test_k2_level_jumps_between_calls_are_redone_with_the_exact_scale():
         err = np.abs(y - ref).max(axis=0)
         bar = REL_F32 * np.maximum(peak, prev_peak)
         assert (err <= bar).all(), f"step {step} (level {lv}): worst {np.max(err / np.maximum(peak, prev_peak)):.3e}"
-        if step in (2, 5):   # a level that held for two buffers: the bar is the buffer's own peak again
-            assert_parity(y, ref, REL_F32, f"step {step} (level {lv})") if step == 5 else None
+        if step in (2, 5):   # a level that held for two buffers: the bar is the buffer's own peak again, from the first frame
+            assert_parity(y, ref, REL_F32, f"step {step} (level {lv})")
+        # behind the first two tiles (and the biquad's memory of them) even the buffer that carries the jump is on its own grid
+        assert_parity(y[600:], ref[600:], REL_F32, f"step {step} (level {lv}), outputs 600..")
         prev_peak = peak
     peak, sumsq, frames = gpu.meter_read()
     rp, rs = orc.meter(np.concatenate(refs))
     assert frames == sum(len(r) for r in refs)
     np.testing.assert_allclose(peak, rp, rtol=2e-6)
     np.testing.assert_allclose(sumsq, rs, rtol=2e-6)
+
+
+def test_k2_call_after_a_60_db_drop_starts_clean():
+    # What tools/k2_soak.py found: a channel that is loud in one call and 60 dB down in the next two.  The call that carries the
+    # drop starts from loud history (its first tiles are served on the loud grid, its error bar is the louder peak); with ONE scale
+    # per call the whole call stayed on that grid and the state it left behind put 1e-4 of the quiet channel's peak into the first
+    # outputs of the call after it.  Whole and partial last tiles, a batch and single buffers.
+    ch = 256
+    st = design.config_stages("chain4")
+    for bf, nb in ((4096, 1), (4000, 1), (4096, 3)):
+        gpu, cpu = abi.Chain(ch, st, buffer_frames=bf, max_batch=nb), orc.Chain(ch, st)
+        quiet = np.where(np.arange(ch) % 4 == 1, 1e-3, 1.0)
+        prev_peak = np.zeros(ch)
+        for call, amp in enumerate((np.ones(ch), quiet, quiet, quiet)):
+            total = bf * nb
+            x = signal_input(total, ch, seed=70 + call) * amp
+            ref = cpu.process(x, threads=os.cpu_count() or 1)
+            d_in, d_out = abi.DeviceBuffer(total * ch * 4), abi.DeviceBuffer(total * ch * 4)
+            d_in.upload(x.astype(np.float32))
+            counts = gpu.process_batch_device(d_in.ptr, [bf] * nb, d_out.ptr, total)
+            gpu.sync()
+            assert gpu.last_path()[0] == 2 and sum(counts) == len(ref)
+            y = d_out.download((len(ref), ch), np.float32)
+            peak = np.abs(ref).max(axis=0)
+            err = np.abs(y - ref).max(axis=0)
+            if call == 1:    # the call that carries the drop: held to the louder of the two peaks
+                assert (err <= REL_F32 * np.maximum(peak, prev_peak)).all(), f"bf {bf} x {nb}, call {call}"
+            else:            # every other call, the two after the drop included: its own peak, from the first output frame
+                assert_parity(y, ref, REL_F32, f"bf {bf} x {nb}, call {call}")
+            prev_peak = peak
+        gpu.close()
 
 
 def test_k2_silent_and_tiny_channels():
