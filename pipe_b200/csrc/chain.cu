@@ -255,6 +255,8 @@ static void launch_stream_mode(const StreamParams<T> &p, int grid, int C, cudaSt
 
 // ---- K2 host side --------------------------------------------------------------
 
+constexpr double kTcMaxPoleRadius = 0.994;   // biquads with poles beyond this stay on K1 (see tc_level_ok)
+
 // fixed-point split: scale 2^shift so that |v| <= 2047 and sum|v| <= 8191 (with |x*2^10| <= 2048 every
 // partial sum of the exact accumulator then stays below 2^24)
 static int fixed_shift(const double *v, int n)
@@ -325,6 +327,15 @@ static int32_t build_tc_tables(pb_chain *c, Segment &s, int acc0 = 0, Segment::T
             e2 += y * y;
         }
         s.tc_level_ok = std::isfinite(e2) && std::sqrt(e2) >= 0.5;
+        // K2 hands the biquad state from block to block as floats (6e-8 of the state).  After a large level drop that rounding stands
+        // against the quiet signal for as long as the filter remembers the loud one, so filters with a long memory -- poles beyond
+        // |z| = 0.994, i.e. more than ~1150 samples for 60 dB: a 40 Hz high-pass at 48 kHz -- stay on K1, whose state is double
+        // (tools/k2_soak.py: 2e-6 .. 7e-6 of the channel's peak behind a 60 dB drop with 40 Hz filters, nothing with the others).
+        {
+            const double a1 = s.a[0], a2 = s.a[1], disc = a1 * a1 - 4.0 * a2;
+            const double radius = disc < 0.0 ? std::sqrt(std::fabs(a2)) : 0.5 * (std::fabs(a1) + std::sqrt(disc));
+            if (!(radius <= kTcMaxPoleRadius)) s.tc_level_ok = false;
+        }
     }
     // MMA2: P = blockdiag(G16) * R.  R[row][m] = coef[branch(m)][i_m - row] is the polyphase matrix of one tile (row = frame + 15;
     // output m is triggered by tile-relative frame i_m = ceil((m+1)*160/147) - 1 with branch 146 - ((i_m+1)*147 % 160)); G16 is the

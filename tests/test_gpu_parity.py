@@ -419,7 +419,10 @@ def test_k2_mutation_and_reset():
 
 
 @pytest.mark.parametrize("kind,f0,q,n_taps,path", [("highpass", 200.0, 0.707, 257, 2), ("lowpass", 8000.0, 0.9, 33, 2),
-                                                   ("peaking", 1000.0, 4.0, 129, 2), ("lowpass", 120.0, 0.6, 257, 1)])
+                                                   ("peaking", 1000.0, 4.0, 129, 2), ("lowpass", 120.0, 0.6, 257, 1),
+                                                   # poles at |z| = 0.9963: a memory of thousands of samples stays on the kernel
+                                                   # whose biquad state is double
+                                                   ("highpass", 40.0, 0.707, 257, 1)])
 def test_k2_other_filters(kind, f0, q, n_taps, path):
     # the biquad is folded per 16-row block into the resampler matrix and its state enters as a rank-2 correction:
     # poles close to z = 1 (slow state decay) and short FIRs must hold the same bar.  A biquad that removes most of a

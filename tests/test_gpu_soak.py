@@ -1,0 +1,18 @@
+"""Randomised parity soak of the tcgen05 chain kernel against the CPU oracle (tools/k2_soak.py): random filters, channel counts,
+call lengths (whole and partial last tiles, batches and single buffers), per-channel levels from 0 to -60 dBFS that jump between
+calls.  The bar is the one of the parity tests: 1e-6 of every channel's own peak per call.  Two seeds here; the tool takes any."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("seed", [3, 8])
+def test_k2_randomised_soak(seed):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k2_soak.py"), "12", str(seed)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok" in r.stdout.splitlines()[-1]

@@ -29,7 +29,8 @@ for it in range(iters):
     bf = int(rng.choice([1600, 4096, 4000, 1000]))
     nb = int(rng.choice([1, 1, 3, 5]))
     meter = bool(rng.integers(0, 2))
-    gpu = abi.Chain(ch, stages, buffer_frames=bf, max_batch=nb, dtype=np.float32, flags=abi.CHAIN_METER if meter else 0)
+    gpu = abi.Chain(ch, stages, buffer_frames=bf, max_batch=nb, dtype=np.float32,
+                    flags=(abi.CHAIN_METER if meter else 0) | (abi.CHAIN_NO_TENSOR if os.environ.get("SOAK_K1") else 0))
     cpu = orc.Chain(ch, stages)
     levels = 10.0 ** (-rng.integers(0, 4, size=ch) * 1.0)           # 0, -20, -40, -60 dBFS per channel
     prev_levels = levels
