@@ -16,3 +16,10 @@ def test_k2_randomised_soak(seed):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k2_soak.py"), "12", str(seed)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok" in r.stdout.splitlines()[-1]
+
+
+def test_k3_randomised_soak():
+    # the streaming kernels: gain + biquad, 1..160 channels, f32 and f64, both sides of the two-sweep threshold, ragged buffers
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k3_soak.py"), "16", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok" in r.stdout.splitlines()[-1]
