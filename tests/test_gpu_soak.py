@@ -23,3 +23,10 @@ def test_k3_randomised_soak():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k3_soak.py"), "16", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok" in r.stdout.splitlines()[-1]
+
+
+def test_k1_randomised_soak():
+    # the generic fused tile kernel: random stage lists in one or two fused segments, resampler ratios, 1..130 channels, f32 and f64
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k1_soak.py"), "24", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok" in r.stdout.splitlines()[-1]
