@@ -30,3 +30,10 @@ def test_k1_randomised_soak():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k1_soak.py"), "24", "4"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok" in r.stdout.splitlines()[-1]
+
+
+def test_lifecycle_randomised_soak():
+    # random sequences of process / set_stage (mutations) / reset through the C-ABI on the three kernel families, meter included
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ops_soak.py"), "16", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok" in r.stdout.splitlines()[-1]
