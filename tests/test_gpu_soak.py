@@ -37,3 +37,10 @@ def test_lifecycle_randomised_soak():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ops_soak.py"), "16", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok" in r.stdout.splitlines()[-1]
+
+
+def test_insert_processor_randomised_soak():
+    # random gains / biquads / FIRs spliced into running fused runs (pb_chain_insert_stage) against the oracle's stage list
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "insert_soak.py"), "16", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok" in r.stdout.splitlines()[-1]
