@@ -50,11 +50,13 @@ for it in range(iters):
         gpu.sync()
         ref = cpu.process(x, threads=os.cpu_count() or 1)
         assert sum(counts) == len(ref), (counts, len(ref))
+        n_calls += 1
+        if len(ref) == 0:      # (a call too short to trigger an output)
+            continue
         y = d_out.download((sum(counts), ch), np.float32)
         pk = np.abs(ref).max(axis=0)
         err = float((np.abs(y.astype(np.float64) - ref).max(axis=0) / np.maximum(pk, 1e-300)).max()) if len(ref) else 0.0
         path = gpu.last_path()[0]
-        n_calls += 1
         n_k2 += path == 2
         worst = max(worst, err)
         if err > 1e-6:

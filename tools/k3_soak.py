@@ -51,7 +51,7 @@ for it in range(iters):
         paths[path] = paths.get(path, 0) + 1
         n_calls += 1
         # f64: the parity tests hold 1e-12 on steady signals; behind a 60 dB drop with poles at 20 Hz (|z| = 0.998) the double
-        # sub-chunk states carry ~1e-16 of the LOUD state against the quiet signal: up to 2e-9 of its peak, measured here
+        # sub-chunk states carry ~1e-16 of the LOUD state against the quiet signal: up to 6e-9 of its peak, measured here
         bar = 1e-6 if dtype == np.float32 else 1e-8
         if dtype == np.float32:
             worst32 = max(worst32, err)
