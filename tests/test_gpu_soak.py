@@ -44,3 +44,10 @@ def test_insert_processor_randomised_soak():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "insert_soak.py"), "16", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok" in r.stdout.splitlines()[-1]
+
+
+def test_pipelined_host_path_randomised_soak():
+    # pb_chain_submit / pb_chain_collect with two batches in flight, pinned and pageable host memory, synchronous calls in between
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "pipeline_soak.py"), "12", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok" in r.stdout.splitlines()[-1]
