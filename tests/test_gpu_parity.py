@@ -582,6 +582,42 @@ def test_k2_full_batch_at_bench_size():
     d_out.free()
 
 
+def test_k2_chains_of_several_lines_share_one_device():
+    # several Lines on one device: three K2 chains launched round-robin on three streams without a sync in between, so their
+    # persistent grids compete for the SMs (K2's look-back waits on tiles of CTAs that may not be resident yet: it has to make
+    # progress, not run into its bound).  Same stages and input for every chain, so one oracle run checks all of them.
+    import torch
+    ch, bf, nb, rounds, n_chains = 1024, 4096, 6, 3, 3
+    st = design.config_stages("chain4")
+    x = signal_input(bf * nb * rounds, ch, seed=11)
+    cpu = orc.Chain(ch, st)
+    refs = [cpu.process(x[i * bf:(i + 1) * bf], threads=os.cpu_count() or 1) for i in range(nb * rounds)]
+    xf = x.astype(np.float32)
+    d_in = abi.DeviceBuffer(xf.nbytes)
+    d_in.upload(xf)
+    per_round = bf * nb * ch * 4
+    chains = [abi.Chain(ch, st, buffer_frames=bf, max_batch=nb) for _ in range(n_chains)]
+    outs = [abi.DeviceBuffer(xf.nbytes) for _ in range(n_chains)]
+    streams = [torch.cuda.Stream(device=0) for _ in range(n_chains)]
+    counts = [[] for _ in range(n_chains)]
+    for r in range(rounds):
+        for k, g in enumerate(chains):
+            done = sum(counts[k])
+            counts[k] += g.process_batch_device(d_in.ptr + r * per_round, [bf] * nb, outs[k].ptr + done * ch * 4,
+                                                bf * nb * rounds - done, stream=streams[k].cuda_stream)
+    for k, g in enumerate(chains):
+        g.sync(streams[k].cuda_stream)
+        assert counts[k] == [len(r) for r in refs] and g.last_path()[0] == 2
+        y = outs[k].download((sum(counts[k]), ch), np.float32)
+        pos = 0
+        for b, r in enumerate(refs):
+            assert_parity(y[pos:pos + len(r)], r, REL_F32, f"chain {k} buffer {b}")
+            pos += len(r)
+    d_in.free()
+    for o in outs:
+        o.free()
+
+
 # ------------------------------------------- K3: streaming kernels (runs without FIR and resampler) --
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
