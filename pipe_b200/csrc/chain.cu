@@ -738,12 +738,26 @@ static int32_t launch_segment_tc(pb_chain *c, Segment &s, const Segment::TcPhase
         double *mtr = !meter ? nullptr : pass == 0 ? c->d_meter_scratch : c->d_meter;
         p.meter_peak = mtr;
         p.meter_sumsq = mtr ? mtr + c->C : nullptr;
-        if (prof_mode == 1) chain_tc_kernel<1><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
-        else if (prof_mode == 2) chain_tc_kernel<2><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
-        else if (p.dbg != 0) chain_tc_kernel<0, false, true><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);   // development switches (whole tiles only)
-        else if (p.last_frames < kTcFrames) chain_tc_kernel<0, true><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
-        else chain_tc_kernel<0><<<grid, kTcThreads, tc::kSmemBytes, stream>>>(p);
-        PB_CUDA(cudaGetLastError());
+        // Cooperative launch: the static tile schedule makes a CTA's look-back wait on tiles of OTHER CTAs of the grid, so the
+        // whole grid (<= one CTA per SM) has to be resident at once.  A cooperative grid is only started when all of it fits
+        // next to whatever else holds the device's SMs (another chain's kernel on its own stream, another process under MPS):
+        // a late CTA can then no longer leave its successors spinning into the look-back bound.
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = tc::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute coop[1];
+        coop[0].id = cudaLaunchAttributeCooperative;
+        coop[0].val.cooperative = 1;
+        static const bool no_coop = getenv("PB_TC_NO_COOP") != nullptr;   // development: plain launches (timing comparison)
+        cfg.attrs = coop;
+        cfg.numAttrs = no_coop ? 0 : 1;
+        if (prof_mode == 1) PB_CUDA(cudaLaunchKernelEx(&cfg, chain_tc_kernel<1>, p));
+        else if (prof_mode == 2) PB_CUDA(cudaLaunchKernelEx(&cfg, chain_tc_kernel<2>, p));
+        else if (p.dbg != 0) PB_CUDA(cudaLaunchKernelEx(&cfg, (chain_tc_kernel<0, false, true>), p));   // development switches (whole tiles only)
+        else if (p.last_frames < kTcFrames) PB_CUDA(cudaLaunchKernelEx(&cfg, (chain_tc_kernel<0, true>), p));
+        else PB_CUDA(cudaLaunchKernelEx(&cfg, chain_tc_kernel<0>, p));
         c->launches++;
         if (prof_on && pass == 0) {
             PB_CUDA(cudaStreamSynchronize(stream));
@@ -1152,8 +1166,18 @@ static int32_t launch_segment_stream(pb_chain *c, Segment &s, const void *in, in
             mpow(s.st_tile_step, sp.per, sp.Mper);
             mpow(s.st_tile_step, sp.span, sp.Mspan);
         }
-        stream_scan_kernel<<<sgrid, kScanWarps * 32, 0, stream>>>(sp);
-        PB_CUDA(cudaGetLastError());
+        {   // cooperative for the same reason as K2: a block waits for the blocks in front of it, the grid must be resident at once
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = sgrid;
+            cfg.blockDim = dim3(kScanWarps * 32);
+            cfg.stream = stream;
+            cudaLaunchAttribute coop[1];
+            coop[0].id = cudaLaunchAttributeCooperative;
+            coop[0].val.cooperative = 1;
+            cfg.attrs = coop;
+            cfg.numAttrs = 1;
+            PB_CUDA(cudaLaunchKernelEx(&cfg, stream_scan_kernel, sp));
+        }
         launch_stream_mode<T, kStApply>(p, grid, c->C, stream);
         PB_CUDA(cudaGetLastError());
         c->launches += 3;
@@ -1464,9 +1488,10 @@ extern "C" int32_t pb_chain_process_batch_device(pb_chain *c, const void *in_dev
                             (cudaStream_t)stream);
 }
 
-// The only kernel-side failure left is a look-back wait that ran into its bound (a tile's predecessors were not scheduled
-// for ~0.3 s: the device is shared with something that holds its SMs).  It is reported once and cleared, so the chain can be
-// reset and used again; what the affected call wrote is undefined.
+// The only kernel-side failure left is a look-back wait that ran into its bound (a tile's predecessors did not publish
+// for seconds).  K1 and the one-sweep K3 claim tiles in ticket order and K2 / the K3 scan are launched cooperatively, so
+// the CTAs a tile waits for are always resident: the bound is a guard against a fault, not a scheduling hazard.  It is
+// reported once and cleared, so the chain can be reset and used again; what the affected call wrote is undefined.
 static int32_t take_kernel_error(pb_chain *c)
 {
     int flag = 0;

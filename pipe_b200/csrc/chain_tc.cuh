@@ -69,7 +69,7 @@
 // the look-back while the first group runs the block-state recursion), warps 18-21 / 22-25 two output groups on the two halves of every slice (D2 -> registers, free the
 // buffer, block-state correction, coalesced stores, meter), warp 26 MMA2 issuer.  Tiles follow a static time-major
 // schedule: the look-back spins on tiles owned by other CTAs of the same grid, so the grid (<= one CTA per SM) must be
-// co-resident -- true whenever the device is not shared with another long-running kernel.  The drain warps hand the 11
+// co-resident -- the host launches the kernel cooperatively (cudaLaunchAttributeCooperative), which starts a grid only when all of it fits.  The drain warps hand the 11
 // block states to the output warps through 24 spare TMEM columns.  Inside a role group only the first warp polls
 // mbarriers, the others wait on a named barrier; the issuing warps run converged and elect one lane per tcgen05
 // instruction.  MMA1 writes the first touch of every 16 columns with accumulate = 0 and waits per column block for the
