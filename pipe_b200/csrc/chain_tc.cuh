@@ -207,6 +207,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// plain bulk copy global -> shared (cp.async.bulk, SASS UBLKCP), completion on an mbarrier; size and addresses multiples of 16
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
     asm volatile(
@@ -362,12 +369,12 @@ constexpr int kOffPark = kOffZx + kZxFloats * 4;                // [128][128] fl
 constexpr int kParkRows = (kRsSlices - 1) * kRsN;               // (the last slice waits in registers: nothing queues behind it)
 constexpr int kOffBar = kOffPark + kParkRows * kTcCh * 4;
 constexpr int kNumBlkBars = kTcChunks - kTcFirstDone;           // 10: one per chunk 17..26
-constexpr int kNumBars = 2 * kRawStages + 2 * kA1Stages + kNumBlkBars + kTcBlocks + kRsSlices + 2 + 1 + 4 + 4 + 4 + 4 + 4;
+constexpr int kNumBars = 2 * kRawStages + 2 * kA1Stages + kNumBlkBars + kTcBlocks + kRsSlices + 2 + 1 + 4 + 4 + 4 + 4 + 4 + 1;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kOffSa = ((kOffTmemSlot + 16 + 15) / 16) * 16;                      // [2][128][2] double: drain group A's chained state of the even blocks (per tile parity)
 constexpr int kSmemBytes = kOffSa + 2 * kTcCh * 2 * 8;
 static_assert(kSmemBytes <= 227 * 1024, "K2 shared memory budget");
-static_assert(kOffTab % 128 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kOffTab % 128 == 0 && kOffBar % 8 == 0 && kTabBytes % 16 == 0 && kRcBytes % 16 == 0, "alignment");
 
 // TMEM columns: D1 = E [0,176) + X [176,352) -- block b's 16 E columns are overwritten in place by the pieces of F (f0: 8
 // columns, f1: 8 columns), the A operand of MMA2; ring of 8 converted chunks (A operand of MMA1: x0 8 columns, x1 8 columns) from
@@ -528,6 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     uint64_t *szs_ready = zx_ready + 4;             // [4]  drain warp A -> drain warp B: zero-state block states and s10 are in the mailbox
     uint64_t *zx_free = szs_ready + 4;              // [4]  drain warp A -> drain warp B: the previous tile's Z have been read
     uint64_t *sa_ready = zx_free + 4;               // [4]  drain warp A -> drain warp B: the chained state of the even blocks 0..8 is in shared memory
+    uint64_t *tab_ready = sa_ready + 4;             //      bulk copies of the B tables and the correction table -> both MMA issuers, output warps
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffTmemSlot);
     double *sa_s = reinterpret_cast<double *>(smem + kOffSa);
 
@@ -602,17 +610,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             mbar_init(&zx_free[i], 1);
             mbar_init(&sa_ready[i], 1);
         }
+        mbar_init(tab_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
+        // the tables arrive by bulk copy behind the CTA's back: the producer and the converters start on the first chunks at
+        // once, only the two MMA issuers and the output warps wait for tab_ready (was: a copy loop of all threads in front of
+        // the first __syncthreads)
+        mbar_expect_tx(tab_ready, kTabBytes + kRcBytes);
+        bulk_load(tab, p.tables, kTabBytes, tab_ready);
+        bulk_load(smem + kOffRc, p.rc, kRcBytes, tab_ready);
     }
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.tables);
-        uint4 *dst = reinterpret_cast<uint4 *>(tab);
-        for (int i = tid; i < kTabBytes / 16; i += kTcThreads) dst[i] = src[i];
-        const float4 *rsrc = reinterpret_cast<const float4 *>(p.rc);
-        float4 *rdst = reinterpret_cast<float4 *>(smem + kOffRc);
-        for (int i = tid; i < kRcBytes / 16; i += kTcThreads) rdst[i] = rsrc[i];
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         // [16q-257, 16q+14], i.e. 8-column blocks [2q-33, 2q+1] clipped to [0, 21] and widened to an even count (N % 16 == 0).
         // The warp runs the loop converged and elects one lane per issue.
         {
+            mbar_wait(tab_ready, 0);
             const uint32_t t0 = smem_u32(tab);
             const uint64_t bd0 = make_desc(t0, 128, 128), bd1 = make_desc(t0 + TcTables::kT * 2, 128, 128);
             const uint64_t bd2 = make_desc(t0 + TcTables::kT * 4, 128, 128), bd3 = make_desc(t0 + TcTables::kT * 6, 128, 128);
@@ -1131,6 +1138,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
         long long r_w = 0, r_m = 0, o_ld = 0, o_out = 0;
         int it = 0;
         unsigned nsl = 0;  // running slice number: phase of the D2 barriers
+        mbar_wait(tab_ready, 0);   // the correction table (rcs)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int t = tile / p.n_cg, cg = tile - t * p.n_cg;
             const bool first = (t == 0), part_tile = PARTIAL && (t == p.n_tiles - 1) && p.last_frames < kTcFrames;
@@ -1245,6 +1253,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
     } else {
         // ================================ MMA2 issuer =================================
         {
+            mbar_wait(tab_ready, 0);
             const uint32_t b2 = smem_u32(tab) + TcTables::kHalfs * 2;
             constexpr uint32_t idesc32 = make_idesc(kRsN), idesc64 = make_idesc(2 * kRsN);
             unsigned nsl = 0;
