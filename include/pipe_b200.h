@@ -108,7 +108,9 @@ int32_t pb_chain_peek_out_frames(const pb_chain *c, int64_t in_frames, int64_t *
 
 /* ProcessFunc(in, out) (int, error) (pipe.go:64, called at pipe.go:438) with
  * host buffers: H2D copy, fused kernel(s), D2H copy, synchronous.  *out_frames
- * is `processed`; a short value is how pipe.go:441-443 slices the output. */
+ * is `processed`; a short value is how pipe.go:441-443 slices the output.
+ * A buffer of 8 MiB or more passes in four pieces so that the copies and the
+ * kernels overlap; the result is that of four consecutive shorter calls. */
 int32_t pb_chain_process(pb_chain *c, const void *in_host, int64_t in_frames,
                          void *out_host, int64_t out_capacity_frames, int64_t *out_frames);
 

@@ -124,6 +124,8 @@ struct pb_chain {
     int last_path = 0;
     int64_t launches = 0;
     std::vector<TmapEntry> tmaps;
+    static constexpr int kMaxPieces = 8;   // pb_chain_process cuts one large host buffer into pieces (process_pieces)
+    cudaEvent_t ev_piece[3][kMaxPieces] = {};   // [h2d | done | d2h][piece]
 };
 
 namespace pb {
@@ -1335,6 +1337,9 @@ extern "C" int32_t pb_chain_destroy(pb_chain *c)
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
     }
+    for (auto &row : c->ev_piece)
+        for (auto &ev : row)
+            if (ev) cudaEventDestroy(ev);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_meter) cudaFree(c->d_meter);
     if (c->d_meter_scratch) cudaFree(c->d_meter_scratch);
@@ -1624,6 +1629,82 @@ extern "C" int32_t pb_chain_collect(pb_chain *c, int64_t *buf_out_frames, int32_
     return kerr;
 }
 
+// ONE large host buffer (the ProcessFunc call of pipe.go:438: synchronous, nothing else in flight) cut into pieces that follow
+// each other through H2D -> kernels -> D2H on the chain's three streams: the copy of piece i+1 in, the kernels of piece i and
+// the copy of piece i-1 out overlap (PCIe is full duplex), and for pageable callers so do the staging memcpys on the host.  To the chain a piece is a call
+// of its own (the carried state crosses calls by construction; pieces are multiples of K2's 160-frame tile, so the resampler
+// phase at the start of every piece is the phase at the start of the buffer).  Measured per 4096 x 1024 buffer from pinned memory
+// (tools/process_time.py): K2 f32 0.651 -> 0.541 ms, K3 f32 0.653 -> 0.522 ms, K1 f64 1.83 -> 1.00 ms; eight pieces are slower than four.
+static int32_t process_pieces(pb_chain *c, const char *in_host, int64_t in_frames, char *out_host, int64_t out_capacity_frames,
+                              int64_t *out_frames, int64_t piece)
+{
+    DeviceGuard dg(c->device);
+    PB_CUDA(dg.err);
+    Slot &sl = c->slots[c->slot_head];
+    int32_t r = ensure_slot(c, sl);
+    if (r != PB_OK) return r;
+    // validate the whole call before anything is enqueued: a rejected call must leave the carried state untouched
+    int64_t tin = 0, tout_need = 0;
+    count_outputs(c, &in_frames, 1, nullptr, &tin, &tout_need, false);
+    if (tout_need > out_capacity_frames)
+        return fail(PB_ERR_CAPACITY, "pb_chain_process: output needs %lld frames, capacity %lld", (long long)tout_need, (long long)out_capacity_frames);
+    if (!in_host || !out_host) return fail(PB_ERR_INVALID, "pb_chain_process: NULL buffer");
+    const bool pin_in = is_pinned(in_host), pin_out = is_pinned(out_host);
+    const size_t slot_bytes = c->elem * (size_t)c->max_frames * c->C, frame_bytes = c->elem * (size_t)c->C;
+    if (!pin_in && !sl.h_in) PB_CUDA(cudaMallocHost(&sl.h_in, slot_bytes));
+    if (!pin_out && !sl.h_out) PB_CUDA(cudaMallocHost(&sl.h_out, slot_bytes));
+    const int n_pieces = (int)((in_frames + piece - 1) / piece);
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < n_pieces; i++)
+            if (!c->ev_piece[k][i]) PB_CUDA(cudaEventCreateWithFlags(&c->ev_piece[k][i], cudaEventDisableTiming));
+    int64_t out_done[pb_chain::kMaxPieces + 1] = {0};
+    int32_t rc = PB_OK;
+    int enq = 0;
+    for (int i = 0; i < n_pieces && rc == PB_OK; i++) {
+        const int64_t f0 = (int64_t)i * piece, n = std::min(piece, in_frames - f0);
+        const size_t off = (size_t)f0 * frame_bytes, nbytes = (size_t)n * frame_bytes;
+        const char *src = in_host + off;
+        if (!pin_in) {
+            memcpy((char *)sl.h_in + off, src, nbytes);
+            src = (const char *)sl.h_in + off;
+        }
+        auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == PB_OK) rc = fail(PB_ERR_CUDA, "pb_chain_process: %s", cudaGetErrorString(e)); };
+        cu(cudaMemcpyAsync((char *)sl.d_in + off, src, nbytes, cudaMemcpyHostToDevice, c->st_h2d));
+        cu(cudaEventRecord(c->ev_piece[0][i], c->st_h2d));
+        cu(cudaStreamWaitEvent(c->st_compute, c->ev_piece[0][i], 0));
+        if (rc != PB_OK) break;
+        int64_t cnt = 0;
+        const size_t ooff = (size_t)out_done[i] * frame_bytes;
+        rc = run_batch_device(c, (const char *)sl.d_in + off, &n, 1, (char *)sl.d_out + ooff, c->max_frames - out_done[i], &cnt, c->st_compute);
+        if (rc != PB_OK) break;
+        out_done[i + 1] = out_done[i] + cnt;
+        cu(cudaEventRecord(c->ev_piece[1][i], c->st_compute));
+        cu(cudaStreamWaitEvent(c->st_d2h, c->ev_piece[1][i], 0));
+        if (cnt) cu(cudaMemcpyAsync((pin_out ? out_host : (char *)sl.h_out) + ooff, (char *)sl.d_out + ooff, (size_t)cnt * frame_bytes, cudaMemcpyDeviceToHost, c->st_d2h));
+        cu(cudaEventRecord(c->ev_piece[2][i], c->st_d2h));
+        enq = i + 1;
+    }
+    // drain piece by piece (a pageable destination is filled while the later pieces are still on their way)
+    for (int i = 0; i < enq; i++) {
+        const cudaError_t e = cudaEventSynchronize(c->ev_piece[2][i]);
+        if (e != cudaSuccess && rc == PB_OK) rc = fail(PB_ERR_CUDA, "pb_chain_process: %s", cudaGetErrorString(e));
+        if (rc == PB_OK && !pin_out && out_done[i + 1] > out_done[i])
+            memcpy(out_host + (size_t)out_done[i] * frame_bytes, (char *)sl.h_out + (size_t)out_done[i] * frame_bytes,
+                   (size_t)(out_done[i + 1] - out_done[i]) * frame_bytes);
+    }
+    if (rc != PB_OK) {
+        cudaStreamSynchronize(c->st_h2d);
+        cudaStreamSynchronize(c->st_compute);
+        cudaStreamSynchronize(c->st_d2h);
+        return rc;
+    }
+    PB_CUDA(cudaEventRecord(sl.ev_d2h, c->st_d2h));   // the slot protocol of submit / collect: this slot's last D2H
+    r = take_kernel_error(c);
+    if (r != PB_OK) return r;
+    if (out_frames) *out_frames = out_done[enq];
+    return PB_OK;
+}
+
 extern "C" int32_t pb_chain_process(pb_chain *c, const void *in_host, int64_t in_frames, void *out_host,
                                     int64_t out_capacity_frames, int64_t *out_frames)
 {
@@ -1631,6 +1712,17 @@ extern "C" int32_t pb_chain_process(pb_chain *c, const void *in_host, int64_t in
     if (c->slots_busy) return fail(PB_ERR_STATE, "pb_chain_process while submitted batches are in flight");
     // A single call may carry up to max_batch buffers' worth of frames.
     if (in_frames < 0 || in_frames > c->max_frames) return fail(PB_ERR_INVALID, "pb_chain_process: %lld frames", (long long)in_frames);
+    {
+        // one buffer of >= 8 MiB whose rows keep every piece 16-byte aligned: four pieces (multiples of 160 frames) in a row
+        static const int want = getenv("PB_PROCESS_PIECES") ? atoi(getenv("PB_PROCESS_PIECES")) : 4;   // 1: off (development)
+        const size_t frame_bytes = c->elem * (size_t)c->C;
+        if (want > 1 && want <= pb_chain::kMaxPieces && in_frames <= c->buffer_frames && frame_bytes % 16 == 0 &&
+            (size_t)in_frames * frame_bytes >= ((size_t)8 << 20)) {
+            const int64_t piece = ((in_frames + want - 1) / want + kTcFrames - 1) / kTcFrames * kTcFrames;
+            if (piece < in_frames)
+                return process_pieces(c, (const char *)in_host, in_frames, (char *)out_host, out_capacity_frames, out_frames, piece);
+        }
+    }
     std::vector<int64_t> bf;
     int64_t left = in_frames;
     do {

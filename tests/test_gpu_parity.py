@@ -618,6 +618,40 @@ def test_k2_chains_of_several_lines_share_one_device():
         o.free()
 
 
+@pytest.mark.parametrize("cfg,channels,dtype", [("chain4", 1024, np.float32), ("chain4", 512, np.float64),
+                                                ("gain_biquad", 1024, np.float32)])
+def test_large_host_buffers_go_through_in_pieces(cfg, channels, dtype):
+    # pb_chain_process cuts one host buffer of >= 8 MiB into four pieces (multiples of 160 frames) that follow each other through
+    # H2D, kernels and D2H; to the chain every piece is a call of its own.  All three kernel families, pageable buffers (numpy) and
+    # a pinned pair, a short last buffer; frame counts bit-exact, every buffer against the oracle.
+    bf = 4096
+    st = design.config_stages(cfg)
+    gpu, cpu = abi.Chain(channels, st, buffer_frames=bf, dtype=dtype), orc.Chain(channels, st)
+    rel = REL_F32 if dtype == np.float32 else REL_F64
+    sizes = [bf, bf, bf, 3000]
+    x = signal_input(sum(sizes), channels, seed=21)
+    item = np.dtype(dtype).itemsize
+    pin_in, pin_out = abi.PinnedBuffer(bf * channels * item), abi.PinnedBuffer(bf * channels * item)
+    pos, _, l0 = 0, *gpu.last_path()
+    for b, n in enumerate(sizes):
+        blk = x[pos:pos + n]
+        pos += n
+        ref = cpu.process(blk, threads=os.cpu_count() or 1)
+        if b % 2 == 0:
+            y = gpu.process(blk.astype(dtype))                       # pageable in and out
+        else:
+            pin_in.array((n, channels), dtype)[:] = blk
+            got = abi._i64()
+            abi.check(abi.lib().pb_chain_process(gpu._h, pin_in.ptr, n, pin_out.ptr, bf, abi.C.byref(got)))
+            y = pin_out.array((bf, channels), dtype)[:got.value].copy()
+        assert len(y) == len(ref)
+        assert_parity(y, ref, rel, f"buffer {b} ({n} frames)")
+    path, l1 = gpu.last_path()
+    assert l1 - l0 >= 4 * len(sizes)                                   # at least one launch per piece
+    pin_in.free()
+    pin_out.free()
+
+
 # ------------------------------------------- K3: streaming kernels (runs without FIR and resampler) --
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
