@@ -637,6 +637,13 @@ def test_large_host_buffers_go_through_in_pieces(cfg, channels, dtype):
         blk = x[pos:pos + n]
         pos += n
         ref = cpu.process(blk, threads=os.cpu_count() or 1)
+        if b == 2:
+            # a call whose output does not fit is rejected before anything is enqueued: the carried state is untouched and the
+            # same buffer, offered again with room, gives the oracle's result
+            pin_in.array((n, channels), dtype)[:] = blk
+            got = abi._i64()
+            rc = abi.lib().pb_chain_process(gpu._h, pin_in.ptr, n, pin_out.ptr, len(ref) - 1, abi.C.byref(got))
+            assert rc == abi.PB_ERR_CAPACITY
         if b % 2 == 0:
             y = gpu.process(blk.astype(dtype))                       # pageable in and out
         else:
