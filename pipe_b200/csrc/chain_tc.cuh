@@ -560,12 +560,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) chain_tc_kernel(const __grid_co
             const float pk = __uint_as_float(p.peak[c]), su = p.scale[c];
             const float units = pk * su;
             bad |= (units > kSigHi) || (pk > 0.f && units < kSigLo);
-            const float ns = pk > 0.f ? fminf(kSigTarget / pk, kSigCap) : su;
-            p.scale_next[c] = ns;
-            p.scale_next[2 * p.C + c] = 1.0f / ns;
-            p.peak_next[c] = 0u;
         }
         const int rerun = __syncthreads_or(bad);
+        // the scales for the next call: written by CTA 0 alone in the steady state (148 CTAs storing the same 24 KB were most of
+        // this launch's time); when the call is redone every CTA writes them (the same values) and reads its own copy back
+        if (rerun || blockIdx.x == 0) {
+            for (int c = tid; c < 2 * p.C; c += kTcThreads) {
+                const float pk = __uint_as_float(p.peak[c]), su = p.scale[c];
+                const float ns = pk > 0.f ? fminf(kSigTarget / pk, kSigCap) : su;
+                p.scale_next[c] = ns;
+                p.scale_next[2 * p.C + c] = 1.0f / ns;
+                p.peak_next[c] = 0u;
+            }
+            if (rerun) __syncthreads();
+        }
         if (blockIdx.x == 0 && p.meter_scratch) {
             // what pass A metered: fold it into the chain's meter, or drop it when the call is redone
             for (int c = tid; c < p.C; c += kTcThreads) {
