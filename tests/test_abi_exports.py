@@ -68,3 +68,21 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "_oracle" not in text and "pipe_oracle" not in text and "liboracle" not in text, f
+
+
+def test_go_shim_uses_only_what_the_header_declares():
+    # go/pipeb200.go cannot be compiled here (no Go toolchain): at least every C.<name> it refers to must exist in the header --
+    # entry points, enum constants, struct types and the struct fields it fills.
+    go = open(os.path.join(ROOT, "go", "pipeb200.go")).read()
+    hdr = open(os.path.join(ROOT, "include", "pipe_b200.h")).read()
+    used = set(re.findall(r"\bC\.((?:pb_|PB_)[A-Za-z0-9_]+)", go))
+    assert {"pb_chain_create", "pb_chain_process", "pb_chain_reset", "pb_chain_sync", "pb_chain_destroy", "pb_last_error"} <= used
+    for name in sorted(used):
+        assert re.search(r"\b%s\b" % re.escape(name), hdr), f"go/pipeb200.go uses C.{name}, not in include/pipe_b200.h"
+    body = re.search(r"typedef struct pb_chain_desc \{(.*?)\} pb_chain_desc;", hdr, flags=re.S)
+    assert body, "pb_chain_desc not found in the header"
+    fields = set(re.findall(r"\b([a-z_]+)\s*(?:\[[0-9]+\])?;", body.group(1)))
+    lit = re.search(r"C\.pb_chain_desc\{(.*?)\n\t\t\}", go, flags=re.S)
+    assert lit, "pb_chain_desc literal not found in the shim"
+    for f in re.findall(r"\b([a-z_]+):", lit.group(1)):
+        assert f in fields, f"go shim fills pb_chain_desc.{f}, which the header does not have"
